@@ -1,0 +1,83 @@
+"""Pins oracle/dn_oracle.py against outputs of the unmodified reference
+(tests/golden/*.npz, written by oracle/make_golden.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, golden_params, ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import dn_oracle as O  # noqa: E402
+
+
+def ops_of(fx, dtype, prefix=""):
+    V = fx[prefix + "mass"].shape[0]
+    rows, cols = fx[prefix + "g_rows"].astype(np.int64), fx[prefix + "g_cols"].astype(np.int64)
+    gX = O.coo_to_csr(rows, cols, fx[prefix + "gx_vals"].astype(dtype), (V, V))
+    gY = O.coo_to_csr(rows, cols, fx[prefix + "gy_vals"].astype(dtype), (V, V))
+    return (fx[prefix + "mass"].astype(dtype), fx[prefix + "evals"].astype(dtype),
+            fx[prefix + "evecs"].astype(dtype), gX, gY)
+
+
+@pytest.mark.parametrize("name,kw", [("block_small", {}), ("block_norot", {}),
+                                     ("block_nograd", {"with_gradient_features": False})])
+def test_block_matches_reference(name, kw):
+    base = load_golden("block_small")
+    fx = load_golden(name)
+    for tag, dt, tol in (("f64", np.float64, 1e-12), ("f32", np.float32, 2e-6)):
+        mass, evals, evecs, gX, gY = ops_of(base, dt)
+        p = golden_params(fx, dt)
+        out, inter = O.diffusion_net_block(fx["x_in"].astype(dt), mass, evals, evecs, gX, gY, p,
+                                           return_intermediates=True, **kw)
+        assert O.rel_err(inter["x_diffuse"], fx["x_diffuse_" + tag]) < tol
+        if "x_grad_features_" + tag in fx:
+            assert O.rel_err(inter["x_grad_features"], fx["x_grad_features_" + tag]) < tol * 20
+        assert O.rel_err(out, fx["out_" + tag]) < tol
+        assert out.dtype == dt
+
+
+def test_clamp_matches_reference():
+    fx = load_golden("block_small")
+    t = golden_params(fx)["diffusion.diffusion_time"]
+    assert t[3] < 0
+    mass, evals, evecs, _, _ = ops_of(fx, np.float32)
+    _, tc = O.learned_time_diffusion(fx["x_in"], mass, evals, evecs, t)
+    np.testing.assert_array_equal(tc, fx["time_after_f32"])
+    assert tc[3] == np.float32(1e-8)
+
+
+def test_k128_block():
+    fx = load_golden("block_k128")
+    mass, evals, evecs, gX, gY = ops_of(fx, np.float64)
+    out, inter = O.diffusion_net_block(fx["x_in"].astype(np.float64), mass, evals, evecs, gX, gY,
+                                       golden_params(fx, np.float64), return_intermediates=True)
+    assert O.rel_err(inter["x_diffuse"], fx["x_diffuse_f64_as32"]) < 2e-7
+    assert O.rel_err(out, fx["out_f64_as32"]) < 2e-7
+
+
+@pytest.mark.parametrize("mode", ["vertices", "edges", "faces", "global_mean"])
+def test_net_matches_reference(mode):
+    fx = load_golden("net_small")
+    mass, evals, evecs, gX, gY = ops_of(fx, np.float64, "m0_")
+    out = O.diffusion_net(fx["verts0"].astype(np.float64), mass, evals, evecs, gX, gY,
+                          golden_params(fx, np.float64), n_block=2, outputs_at=mode,
+                          faces=fx["faces"].astype(np.int64), edges=fx["edges"].astype(np.int64))
+    assert O.rel_err(out, fx["out_{}_f64".format(mode)]) < 1e-12
+
+
+def test_batch_equals_per_mesh():
+    fx = load_golden("net_small")
+    p = golden_params(fx, np.float64)
+    for b, pre in enumerate(("m0_", "m1_")):
+        mass, evals, evecs, gX, gY = ops_of(fx, np.float64, pre)
+        out = O.diffusion_net(fx["verts{}".format(b)].astype(np.float64), mass, evals, evecs, gX, gY, p, n_block=2)
+        assert O.rel_err(out, fx["out_batch2_f64"][b]) < 1e-12
+
+
+def test_wrong_channels_raises():
+    fx = load_golden("block_small")
+    mass, evals, evecs, gX, gY = ops_of(fx, np.float32)
+    with pytest.raises(ValueError):
+        O.diffusion_net_block(fx["x_in"][:, :5], mass, evals, evecs, gX, gY, golden_params(fx))
