@@ -1,0 +1,454 @@
+// C-ABI entry points (include/diffusion_net_b200.h).  Argument checking, workspace carving and
+// the kernel sequence of each reference function; no torch types, no hidden synchronisation.
+#include "dn_internal.h"
+#include <string.h>
+
+namespace {
+
+struct Bump {
+  char* base;
+  int64_t size, off;
+  Bump(void* p, int64_t n) : base(static_cast<char*>(p)), size(n), off(0) {}
+  float* take(int64_t floats) {
+    const int64_t bytes = (floats * 4 + 255) / 256 * 256;
+    if (!base || off + bytes > size) return nullptr;
+    float* r = reinterpret_cast<float*>(base + off);
+    off += bytes;
+    return r;
+  }
+  int64_t left_floats() const { return (size - off) / 4; }
+};
+
+constexpr int64_t kPartialFloats = 16ll << 20;  // 64 MiB split-V partial sums
+
+inline bool use_tc(int engine) { return engine == DN_ENGINE_TC3X || engine == DN_ENGINE_TC1X; }
+inline int tc_passes(int engine) { return engine == DN_ENGINE_TC1X ? 1 : 3; }
+
+inline DnLayer make_layer(const float* W, int64_t ldw, int w_trans, const float* bias, int relu, int K, int N,
+                          float* out, int64_t ld_out) {
+  DnLayer L;
+  memset(&L, 0, sizeof(L));
+  L.W = W; L.ldw = ldw; L.w_trans = w_trans; L.bias = bias; L.relu = relu; L.K = K; L.N = N;
+  L.out = out; L.ld_out = ld_out; L.res_scale = 1.f;
+  return L;
+}
+
+inline DnRowsSrc one_src(const float* p, int width, int64_t ld) {
+  DnRowsSrc s;
+  memset(&s, 0, sizeof(s));
+  s.ptr[0] = p; s.width[0] = width; s.ld[0] = ld; s.nsrc = 1;
+  return s;
+}
+
+// run a chain of layers; tensor-core engine when it supports the shapes, exact SIMT otherwise.
+// `tmp0/tmp1` are V x maxN ping-pong buffers used only by the unfused SIMT route.
+int run_chain(const DnRowsSrc& src, DnLayer* layers, int n_layers, int64_t V, int engine, float* tmp0,
+              float* tmp1, void* tc_ws, int64_t tc_ws_bytes, cudaStream_t st) {
+  if (use_tc(engine) && tc_supported_device() && tc_rows_chain_supported(src, layers, n_layers) == DN_OK) {
+    return tc_rows_chain(src, layers, n_layers, V, tc_passes(engine), tc_ws, tc_ws_bytes, st);
+  }
+  DnRowsSrc cur = src;
+  for (int l = 0; l < n_layers; ++l) {
+    DnLayer L = layers[l];
+    float* o = L.out;
+    int64_t ldo = L.ld_out;
+    if (!o) {
+      o = (l & 1) ? tmp1 : tmp0;
+      ldo = L.N;
+      if (!o) return DN_ERR_WORKSPACE;
+    }
+    L.out = o; L.ld_out = ldo;
+    int rc = simt_rows_gemm(cur, L, V, st);
+    if (rc) return rc;
+    cur = one_src(o, L.N, ldo);
+  }
+  return DN_OK;
+}
+
+int to_basis_partials(const float* values, const float* basis, const float* massvec, int64_t V, int K, int C,
+                      float* partial, int64_t partial_floats, int* P, int engine, cudaStream_t st) {
+  if (use_tc(engine) && tc_supported_device() && tc_to_basis_supported(K, C) == DN_OK &&
+      (int64_t)148 * K * C <= partial_floats) {
+    return tc_to_basis_partial(values, basis, massvec, V, K, C, partial, P, tc_passes(engine), st);
+  }
+  // out[k][c] = sum_v basis[v][k] * (mass[v] * values[v][c])
+  return simt_atb_partial_st(basis, K, K, values, C, C, massvec, V, partial, partial_floats, P, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dn_abi_version(void) { return DN_ABI_VERSION; }
+
+const char* dn_error_string(int code) {
+  switch (code) {
+    case DN_OK: return "ok";
+    case DN_ERR_INVALID_ARGUMENT: return "diffusion_net_b200: invalid argument";
+    case DN_ERR_UNSUPPORTED: return "diffusion_net_b200: unsupported shape/engine";
+    case DN_ERR_WORKSPACE: return "diffusion_net_b200: workspace too small (see dn_workspace_bytes)";
+    case DN_ERR_NOT_SM100: return "diffusion_net_b200: tensor-core engine needs an sm_100 GPU";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+  return "diffusion_net_b200: unknown error";
+}
+
+int dn_device_query(int device, int* sm_count, int* cc, int64_t* smem_optin_bytes) {
+  cudaDeviceProp p;
+  DN_CUDA_TRY(cudaGetDeviceProperties(&p, device));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc) *cc = p.major * 10 + p.minor;
+  if (smem_optin_bytes) *smem_optin_bytes = (int64_t)p.sharedMemPerBlockOptin;
+  return DN_OK;
+}
+
+int64_t dn_workspace_bytes(int64_t V, int K, int C) {
+  if (V < 0 || K < 0 || C <= 0) return -1;
+  const int64_t vc = ((V + 127) / 128 * 128) * (int64_t)C * 4;
+  return kPartialFloats * 4 + 14 * (vc + 256) + (8ll << 20) + (int64_t)K * C * 16;
+}
+
+int dn_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* vx, const float* vy, int64_t nnz,
+                    int64_t V, int32_t* rowptr, int32_t* colidx, float* vals, dn_stream_t stream) {
+  if (nnz < 0 || V < 0 || !rowptr || (nnz > 0 && (!rows || !cols || !vx || !colidx || !vals)))
+    return DN_ERR_INVALID_ARGUMENT;
+  if (nnz >= (1ll << 31) || V >= (1ll << 31)) return DN_ERR_UNSUPPORTED;
+  return launch_csr_from_coo(rows, cols, vx, vy, nnz, V, rowptr, colidx, vals, (cudaStream_t)stream);
+}
+
+int dn_to_basis(const float* values, const float* basis, const float* massvec, int64_t V, int K, int C, float* out,
+                void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream) {
+  if (!values || !basis || !out || V < 0 || K <= 0 || C <= 0) return DN_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump ws(workspace, ws_bytes);
+  const int64_t pf = ws.left_floats() < kPartialFloats ? ws.left_floats() : kPartialFloats;
+  float* partial = ws.take(pf);
+  if (!partial) return DN_ERR_WORKSPACE;
+  int P = 0;
+  int rc = to_basis_partials(values, basis, massvec, V, K, C, partial, pf, &P, engine, st);
+  if (rc) return rc;
+  return launch_reduce_partials(partial, P, (int64_t)K * C, out, st);
+}
+
+int dn_from_basis(const float* values, const float* basis, const float* row_scale, int64_t V, int K, int C,
+                  float* out, void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream) {
+  if (!values || !basis || !out || V < 0 || K <= 0 || C <= 0) return DN_ERR_INVALID_ARGUMENT;
+  DnRowsSrc src = one_src(basis, K, K);
+  DnLayer L = make_layer(values, C, /*w_trans=*/1, nullptr, 0, K, C, out, C);
+  L.row_scale = row_scale;
+  return run_chain(src, &L, 1, V, engine, nullptr, nullptr, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+int dn_learned_time_diffusion_fwd(const float* x, const float* mass, const float* evals, const float* evecs,
+                                  float* time, int64_t V, int K, int C, float* x_diffuse, float* x_spec_out,
+                                  void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream) {
+  if (!x || !mass || !evals || !evecs || !time || !x_diffuse || V < 0 || K <= 0 || C <= 0)
+    return DN_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump ws(workspace, ws_bytes);
+  float* S = ws.take((int64_t)K * C);
+  const int64_t pf = ws.left_floats() / 2 < kPartialFloats ? ws.left_floats() / 2 : kPartialFloats;
+  float* partial = ws.take(pf);
+  if (!S || !partial) return DN_ERR_WORKSPACE;
+  int P = 0;
+  int rc = to_basis_partials(x, evecs, mass, V, K, C, partial, pf, &P, engine, st);
+  if (rc) return rc;
+  rc = launch_spectral_scale(partial, P, evals, time, K, C, x_spec_out, S, /*clamp_writeback=*/1, st);
+  if (rc) return rc;
+  DnRowsSrc src = one_src(evecs, K, K);
+  DnLayer L = make_layer(S, C, 1, nullptr, 0, K, C, x_diffuse, C);
+  return run_chain(src, &L, 1, V, engine, nullptr, nullptr, ws.base + ws.off, ws.size - ws.off, st);
+}
+
+int dn_learned_time_diffusion_bwd(const float* grad_out, const float* mass, const float* evals, const float* evecs,
+                                  const float* time, const float* x_spec, int64_t V, int K, int C, float* grad_x,
+                                  float* grad_time, void* workspace, int64_t ws_bytes, int engine,
+                                  dn_stream_t stream) {
+  if (!grad_out || !mass || !evals || !evecs || !time || !x_spec || !grad_x || !grad_time)
+    return DN_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump ws(workspace, ws_bytes);
+  float* dS = ws.take((int64_t)K * C);
+  const int64_t pf = ws.left_floats() / 2 < kPartialFloats ? ws.left_floats() / 2 : kPartialFloats;
+  float* partial = ws.take(pf);
+  if (!dS || !partial) return DN_ERR_WORKSPACE;
+  int P = 0;
+  int rc = to_basis_partials(grad_out, evecs, nullptr, V, K, C, partial, pf, &P, engine, st);
+  if (rc) return rc;
+  rc = launch_spectral_bwd(partial, P, evals, time, x_spec, K, C, dS, grad_time, st);
+  if (rc) return rc;
+  DnRowsSrc src = one_src(evecs, K, K);
+  DnLayer L = make_layer(dS, C, 1, nullptr, 0, K, C, grad_x, C);
+  L.row_scale = mass;
+  return run_chain(src, &L, 1, V, engine, nullptr, nullptr, ws.base + ws.off, ws.size - ws.off, st);
+}
+
+int dn_grad_spmm(const dn_csr* grad, const float* x, int64_t V, int C, float* out, dn_stream_t stream) {
+  if (!grad || !grad->rowptr || !x || !out || V < 0 || C <= 0) return DN_ERR_INVALID_ARGUMENT;
+  return launch_grad_spmm_pair(grad, x, V, C, out, (cudaStream_t)stream);
+}
+
+int dn_spatial_gradient_features_fwd(const float* vectors, const float* A_re, const float* A_im,
+                                     int with_gradient_rotations, int64_t V, int C, float* out, void* workspace,
+                                     int64_t ws_bytes, int engine, dn_stream_t stream) {
+  if (!vectors || !A_re || (with_gradient_rotations && !A_im) || !out || V < 0 || C <= 0)
+    return DN_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump ws(workspace, ws_bytes);
+  float* g01 = ws.take(V * 2 * C);
+  float* b01 = ws.take(V * 2 * C);
+  if (!g01 || !b01) return DN_ERR_WORKSPACE;
+  int rc = launch_deinterleave_vc2(vectors, V, C, g01, st);
+  if (rc) return rc;
+  // Bre = g0 A_re^T - g1 A_im^T ; Bim = g1 A_re^T + g0 A_im^T   (layers.py:122-123)
+  DnRowsSrc s0 = one_src(g01, C, 2 * C), s1 = one_src(g01 + C, C, 2 * C);
+  if (with_gradient_rotations) {
+    DnLayer T = make_layer(A_im, C, 0, nullptr, 0, C, C, b01, 2 * C);           // b0 = g1 A_im^T
+    if ((rc = simt_rows_gemm(s1, T, V, st))) return rc;
+    DnLayer L = make_layer(A_re, C, 0, nullptr, 0, C, C, b01, 2 * C);           // b0 = g0 A_re^T - b0
+    L.residual = b01; L.ld_res = 2 * C; L.res_scale = -1.f;
+    if ((rc = simt_rows_gemm(s0, L, V, st))) return rc;
+    DnLayer M = make_layer(A_re, C, 0, nullptr, 0, C, C, b01 + C, 2 * C);       // b1 = g1 A_re^T
+    if ((rc = simt_rows_gemm(s1, M, V, st))) return rc;
+    DnLayer N2 = make_layer(A_im, C, 0, nullptr, 0, C, C, b01 + C, 2 * C);      // b1 = g0 A_im^T + b1
+    N2.residual = b01 + C; N2.ld_res = 2 * C;
+    if ((rc = simt_rows_gemm(s0, N2, V, st))) return rc;
+  } else {
+    DnLayer L = make_layer(A_re, C, 0, nullptr, 0, C, C, b01, 2 * C);           // layers.py:125-126
+    if ((rc = simt_rows_gemm(s0, L, V, st))) return rc;
+    L.out = b01 + C;
+    if ((rc = simt_rows_gemm(s1, L, V, st))) return rc;
+  }
+  (void)engine;
+  return launch_complex_dots_tanh(g01, b01, V, C, out, st);
+}
+
+int dn_gradient_features_fwd(const dn_csr* grad, const float* x_diffuse, const float* A_re, const float* A_im,
+                             int with_gradient_rotations, int64_t V, int C, float* features, float* pq_out,
+                             void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream) {
+  if (!grad || !grad->rowptr || !x_diffuse || !A_re || (with_gradient_rotations && !A_im) || !features || V < 0 ||
+      C <= 0)
+    return DN_ERR_INVALID_ARGUMENT;
+  if (C % 4) return DN_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump ws(workspace, ws_bytes);
+  const int npq = with_gradient_rotations ? 2 * C : C;
+  float* pq = pq_out ? pq_out : ws.take(V * npq);
+  float* wpack = ws.take((int64_t)npq * C);
+  if (!pq || !wpack) return DN_ERR_WORKSPACE;
+  DN_CUDA_TRY(cudaMemcpyAsync(wpack, A_re, sizeof(float) * C * C, cudaMemcpyDeviceToDevice, st));
+  if (with_gradient_rotations)
+    DN_CUDA_TRY(cudaMemcpyAsync(wpack + (int64_t)C * C, A_im, sizeof(float) * C * C, cudaMemcpyDeviceToDevice, st));
+  DnRowsSrc src = one_src(x_diffuse, C, C);
+  DnLayer L = make_layer(wpack, C, 0, nullptr, 0, C, npq, pq, npq);   // [P|Q] = xd [A_re;A_im]^T
+  int rc = run_chain(src, &L, 1, V, engine, nullptr, nullptr, ws.base + ws.off, ws.size - ws.off, st);
+  if (rc) return rc;
+  return launch_spmm_features(grad, x_diffuse, pq, with_gradient_rotations, V, C, features, st);
+}
+
+int dn_gradient_features_bwd(const dn_csr* grad, const dn_csr* grad_t, const float* grad_features,
+                             const float* x_diffuse, const float* pq, const float* features, const float* A_re,
+                             const float* A_im, int with_gradient_rotations, int64_t V, int C, float* grad_x,
+                             float* grad_A_re, float* grad_A_im, void* workspace, int64_t ws_bytes, int engine,
+                             dn_stream_t stream) {
+  if (!grad || !grad_t || !grad_features || !x_diffuse || !pq || !features || !A_re || !grad_x || !grad_A_re ||
+      (with_gradient_rotations && (!A_im || !grad_A_im)))
+    return DN_ERR_INVALID_ARGUMENT;
+  if (C % 4) return DN_ERR_UNSUPPORTED;
+  (void)engine;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump ws(workspace, ws_bytes);
+  const int npq = with_gradient_rotations ? 2 * C : C;
+  float* U = ws.take(V * 4 * C);
+  float* dxd = ws.take(V * C);
+  float* dpq = ws.take(V * npq);
+  float* part = ws.take(kPartialFloats / 4);
+  if (!U || !dxd || !dpq || !part) return DN_ERR_WORKSPACE;
+  int rc;
+  if ((rc = launch_features_bwd_local(grad, x_diffuse, pq, features, grad_features, with_gradient_rotations, V, C,
+                                      U, st)))
+    return rc;
+  if ((rc = launch_features_bwd_transpose(grad_t, U, with_gradient_rotations, V, C, dxd, dpq, st))) return rc;
+  // grad_x = dxd + dP A_re (+ dQ A_im)
+  {
+    DnRowsSrc s = one_src(dpq, C, npq);
+    DnLayer L = make_layer(A_re, C, /*w_trans=*/1, nullptr, 0, C, C, grad_x, C);
+    L.residual = dxd; L.ld_res = C;
+    if ((rc = simt_rows_gemm(s, L, V, st))) return rc;
+    if (with_gradient_rotations) {
+      DnRowsSrc s2 = one_src(dpq + C, C, npq);
+      DnLayer M = make_layer(A_im, C, 1, nullptr, 0, C, C, grad_x, C);
+      M.residual = grad_x; M.ld_res = C;
+      if ((rc = simt_rows_gemm(s2, M, V, st))) return rc;
+    }
+  }
+  // grad_A_re[n][k] += sum_v dP[v][n] xd[v][k]
+  if ((rc = simt_atb(dpq, npq, C, x_diffuse, C, C, nullptr, V, grad_A_re, C, 1, part, kPartialFloats / 4, st)))
+    return rc;
+  if (with_gradient_rotations)
+    if ((rc = simt_atb(dpq + C, npq, C, x_diffuse, C, C, nullptr, V, grad_A_im, C, 1, part, kPartialFloats / 4, st)))
+      return rc;
+  return DN_OK;
+}
+
+int dn_mini_mlp_fwd(const float* const* src_host, const int* src_width_host, int nsrc,
+                    const float* const* weight_host, const float* const* bias_host, const int* dims_host,
+                    int n_layers, const float* const* drop_mask_host, const float* residual, int64_t V,
+                    float* const* hidden_out_host, float* out, void* workspace, int64_t ws_bytes, int engine,
+                    dn_stream_t stream) {
+  if (!src_host || !src_width_host || nsrc < 1 || nsrc > DN_MAX_SRC || !weight_host || !dims_host || n_layers < 1 ||
+      n_layers > DN_MAX_LAYERS || !out || V < 0)
+    return DN_ERR_INVALID_ARGUMENT;
+  DnRowsSrc src;
+  memset(&src, 0, sizeof(src));
+  int k0 = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    if (!src_host[s] || src_width_host[s] <= 0) return DN_ERR_INVALID_ARGUMENT;
+    src.ptr[s] = src_host[s]; src.width[s] = src_width_host[s]; src.ld[s] = src_width_host[s];
+    k0 += src_width_host[s];
+  }
+  src.nsrc = nsrc;
+  if (k0 != dims_host[0]) return DN_ERR_INVALID_ARGUMENT;
+  DnLayer layers[DN_MAX_LAYERS];
+  int maxn = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    if (!weight_host[l] || dims_host[l + 1] <= 0) return DN_ERR_INVALID_ARGUMENT;
+    const bool last = (l + 1 == n_layers);
+    float* o = last ? out : (hidden_out_host ? hidden_out_host[l] : nullptr);
+    layers[l] = make_layer(weight_host[l], dims_host[l], 0, bias_host ? bias_host[l] : nullptr, last ? 0 : 1,
+                           dims_host[l], dims_host[l + 1], o, dims_host[l + 1]);
+    if (!last && drop_mask_host) layers[l].emul = drop_mask_host[l];
+    if (last && residual) { layers[l].residual = residual; layers[l].ld_res = dims_host[l + 1]; }
+    if (dims_host[l + 1] > maxn) maxn = dims_host[l + 1];
+  }
+  Bump ws(workspace, ws_bytes);
+  float *t0 = nullptr, *t1 = nullptr;
+  const bool fused = use_tc(engine) && tc_supported_device() && tc_rows_chain_supported(src, layers, n_layers) == DN_OK;
+  if (!fused && n_layers > 1) {
+    t0 = ws.take(V * maxn);
+    t1 = ws.take(V * maxn);
+    if (!t0 || !t1) return DN_ERR_WORKSPACE;
+  }
+  return run_chain(src, layers, n_layers, V, engine, t0, t1, ws.base + ws.off, ws.size - ws.off,
+                   (cudaStream_t)stream);
+}
+
+int dn_mini_mlp_bwd(const float* grad_out, const float* const* src_host, const int* src_width_host, int nsrc,
+                    const float* const* weight_host, const int* dims_host, int n_layers,
+                    const float* const* hidden_host, const float* const* drop_mask_host, int64_t V,
+                    float* const* grad_src_host, float* const* grad_weight_host, float* const* grad_bias_host,
+                    void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream) {
+  if (!grad_out || !src_host || !src_width_host || nsrc < 1 || nsrc > DN_MAX_SRC || !weight_host || !dims_host ||
+      n_layers < 1 || n_layers > DN_MAX_LAYERS || (n_layers > 1 && !hidden_host) || !grad_src_host ||
+      !grad_weight_host)
+    return DN_ERR_INVALID_ARGUMENT;
+  (void)engine;
+  cudaStream_t st = (cudaStream_t)stream;
+  int maxn = 0;
+  for (int l = 0; l <= n_layers; ++l) maxn = dims_host[l] > maxn ? dims_host[l] : maxn;
+  Bump ws(workspace, ws_bytes);
+  float* d0 = ws.take(V * maxn);
+  float* d1 = ws.take(V * maxn);
+  float* part = ws.take(kPartialFloats / 2);
+  if (!d0 || !d1 || !part) return DN_ERR_WORKSPACE;
+  const float* dz = grad_out;   // gradient w.r.t. the pre-activation of layer l
+  int rc;
+  for (int l = n_layers - 1; l >= 0; --l) {
+    const int nout = dims_host[l + 1], nin = dims_host[l];
+    // weight / bias gradients
+    if (l > 0) {
+      if ((rc = simt_atb(dz, nout, nout, hidden_host[l - 1], nin, nin, nullptr, V, grad_weight_host[l], nin, 1, part,
+                         kPartialFloats / 2, st)))
+        return rc;
+    } else {
+      int off = 0;
+      for (int s = 0; s < nsrc; ++s) {
+        if ((rc = simt_atb(dz, nout, nout, src_host[s], src_width_host[s], src_width_host[s], nullptr, V,
+                           grad_weight_host[0] + off, nin, 1, part, kPartialFloats / 2, st)))
+          return rc;
+        off += src_width_host[s];
+      }
+    }
+    if (grad_bias_host && grad_bias_host[l])
+      if ((rc = simt_colsum(dz, nout, nout, V, grad_bias_host[l], 1, st))) return rc;
+    // input gradient
+    DnRowsSrc s = one_src(dz, nout, nout);
+    if (l > 0) {
+      float* o = (dz == d0) ? d1 : d0;
+      DnLayer L = make_layer(weight_host[l], nin, /*w_trans=*/1, nullptr, 0, nout, nin, o, nin);
+      L.relu_mask_src = hidden_host[l - 1];
+      if (drop_mask_host && drop_mask_host[l - 1]) L.emul = drop_mask_host[l - 1];
+      if ((rc = simt_rows_gemm(s, L, V, st))) return rc;
+      dz = o;
+    } else {
+      int off = 0;
+      for (int q = 0; q < nsrc; ++q) {
+        if (grad_src_host[q]) {
+          DnLayer L = make_layer(weight_host[0] + off, nin, 1, nullptr, 0, nout, src_width_host[q], grad_src_host[q],
+                                 src_width_host[q]);
+          if ((rc = simt_rows_gemm(s, L, V, st))) return rc;
+        }
+        off += src_width_host[q];
+      }
+    }
+  }
+  return DN_OK;
+}
+
+int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const float* evecs, const dn_csr* grad,
+                 const dn_block_params* p, int64_t V, int K, int C, float* out, void* workspace, int64_t ws_bytes,
+                 int engine, dn_stream_t stream) {
+  if (!x_in || !mass || !evals || !evecs || !p || !p->diffusion_time || !out || V < 0 || K <= 0 || C <= 0)
+    return DN_ERR_INVALID_ARGUMENT;
+  if (p->with_gradient_features && (!grad || !grad->rowptr || !p->A_re || (p->with_gradient_rotations && !p->A_im)))
+    return DN_ERR_INVALID_ARGUMENT;
+  if (p->n_mlp_layers < 1 || p->n_mlp_layers > DN_MAX_LAYERS || !p->mlp_weight_host || !p->mlp_dims_host)
+    return DN_ERR_INVALID_ARGUMENT;
+  if (p->with_gradient_features && (C % 4)) return DN_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump ws(workspace, ws_bytes);
+  const int rot = p->with_gradient_rotations;
+  const int npq = rot ? 2 * C : C;
+  float* S = ws.take((int64_t)K * C);
+  float* xd = ws.take(V * C);
+  float* pq = p->with_gradient_features ? ws.take(V * npq) : nullptr;
+  float* feat = p->with_gradient_features ? ws.take(V * C) : nullptr;
+  float* wpack = p->with_gradient_features ? ws.take((int64_t)npq * C) : nullptr;
+  const int64_t pf = kPartialFloats;
+  float* partial = ws.take(pf);
+  if (!S || !xd || !partial || (p->with_gradient_features && (!pq || !feat || !wpack))) return DN_ERR_WORKSPACE;
+  int rc, P = 0;
+  // (a1) spectral diffusion: to_basis -> exp(-lambda t) -> from_basis   [layers.py:56-67]
+  if ((rc = to_basis_partials(x_in, evecs, mass, V, K, C, partial, pf, &P, engine, st))) return rc;
+  if ((rc = launch_spectral_scale(partial, P, evals, p->diffusion_time, K, C, nullptr, S, 1, st))) return rc;
+  void* tcws = ws.base + ws.off;
+  const int64_t tcws_bytes = ws.size - ws.off;
+  {
+    DnRowsSrc src = one_src(evecs, K, K);
+    DnLayer L[2];
+    L[0] = make_layer(S, C, 1, nullptr, 0, K, C, xd, C);
+    int nl = 1;
+    if (p->with_gradient_features) {
+      // (a5, commuted) [P|Q] = x_diffuse [A_re;A_im]^T, fused behind from_basis on the same row tile
+      DN_CUDA_TRY(cudaMemcpyAsync(wpack, p->A_re, sizeof(float) * C * C, cudaMemcpyDeviceToDevice, st));
+      if (rot)
+        DN_CUDA_TRY(cudaMemcpyAsync(wpack + (int64_t)C * C, p->A_im, sizeof(float) * C * C,
+                                    cudaMemcpyDeviceToDevice, st));
+      L[1] = make_layer(wpack, C, 0, nullptr, 0, C, npq, pq, npq);
+      nl = 2;
+    }
+    if ((rc = run_chain(src, L, nl, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
+  }
+  // (a4+a5) sparse tangent gradient + complex inner product + tanh   [layers.py:216-226,128-130]
+  if (p->with_gradient_features)
+    if ((rc = launch_spmm_features(grad, xd, pq, rot, V, C, feat, st))) return rc;
+  // (a6+a7) cat -> MiniMLP -> + x_in   [layers.py:229-239]
+  const float* srcs[3] = {x_in, xd, feat};
+  const int widths[3] = {C, C, C};
+  return dn_mini_mlp_fwd(srcs, widths, p->with_gradient_features ? 3 : 2, p->mlp_weight_host, p->mlp_bias_host,
+                         p->mlp_dims_host, p->n_mlp_layers, nullptr, x_in, V, nullptr, out, tcws, tcws_bytes, engine,
+                         stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// Internal (non-ABI) declarations shared by the SIMT kernels, the tcgen05 kernels and the
+// C-ABI glue.  Everything here is device-pointer based; no torch types anywhere in csrc/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/diffusion_net_b200.h"
+
+#define DN_MAX_SRC 3
+#define DN_MAX_LAYERS 8
+
+#define DN_CUDA_TRY(expr)                          \
+  do {                                             \
+    cudaError_t _e = (expr);                       \
+    if (_e != cudaSuccess) return (int)_e;         \
+  } while (0)
+
+#define DN_LAUNCH_CHECK()                          \
+  do {                                             \
+    cudaError_t _e = cudaGetLastError();           \
+    if (_e != cudaSuccess) return (int)_e;         \
+  } while (0)
+
+// One affine layer applied to 128-row tiles of vertices:  out = epi(A @ W^T + bias)
+//   A = concat_s src[s] (layer 0) -- or the previous layer's output inside a fused chain.
+struct DnLayer {
+  const float* W;        // nn.Linear layout [N][K] (ldw = K) when !w_trans; [K][N] (ldw = N) when w_trans
+  int64_t ldw;
+  int w_trans;
+  const float* bias;     // [N] or null
+  int relu;
+  const float* emul;     // optional elementwise multiplier [V][N] applied after the activation
+  const float* relu_mask_src;  // optional [V][N]: multiply by (src > 0)   (backward of ReLU)
+  const float* row_scale;      // optional [V]: multiply rows (mass, backward of to_basis)
+  const float* residual; // optional [V][N] added last (times res_scale)
+  int64_t ld_res;
+  float res_scale;
+  float* out;            // optional [V][N] (ld_out); null => stays on chip (fused chain only)
+  int64_t ld_out;
+  int K, N;
+};
+
+struct DnRowsSrc {
+  const float* ptr[DN_MAX_SRC];
+  int width[DN_MAX_SRC];
+  int64_t ld[DN_MAX_SRC];
+  int nsrc;
+};
+
+// ---- SIMT engine (dn_simt.cu) ----
+int simt_rows_gemm(const DnRowsSrc& src, const DnLayer& layer, int64_t V, cudaStream_t st);
+// out[i][j] (ld_out) (+)= sum_v A[v][i] * scale[v] * B[v][j];  partial sums staged in ws.
+int simt_atb(const float* A, int64_t lda, int I, const float* B, int64_t ldb, int J, const float* scale,
+             int64_t V, float* out, int64_t ld_out, int accumulate, float* ws, int64_t ws_floats,
+             cudaStream_t st);
+int simt_atb_partial_st(const float* A, int64_t lda, int I, const float* B, int64_t ldb, int J, const float* scale,
+                        int64_t V, float* ws, int64_t ws_floats, int* P_out, cudaStream_t st);
+int simt_colsum(const float* A, int64_t lda, int N, int64_t V, float* out, int accumulate, cudaStream_t st);
+
+// ---- shared small kernels (dn_simt.cu) ----
+// S[k][c] = exp(-evals[k]*max(t[c],1e-8)) * sum_p partial[p][k][c]; optionally writes the raw sum
+// (x_spec) and the clamped time back.  s_trans: write S as [c][k].
+int launch_spectral_scale(const float* partial, int P, const float* evals, float* time, int K, int C,
+                          float* x_spec_out, float* S_out, int clamp_writeback, cudaStream_t st);
+int launch_reduce_partials(const float* partial, int P, int64_t n, float* out, cudaStream_t st);
+int launch_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* vx, const float* vy,
+                        int64_t nnz, int64_t V, int32_t* rowptr, int32_t* colidx, float* vals, cudaStream_t st);
+int launch_grad_spmm_pair(const dn_csr* g, const float* x, int64_t V, int C, float* out_vc2, cudaStream_t st);
+// R-order fused features: feat = tanh(gX*Bre + gY*Bim) from gathers of xd, P, Q (pq = [P|Q], ld 2C or C).
+int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int rotations, int64_t V, int C,
+                         float* feat, cudaStream_t st);
+int launch_features_bwd_local(const dn_csr* g, const float* xd, const float* pq, const float* feat,
+                              const float* dfeat, int rotations, int64_t V, int C, float* U /*V x 4C*/,
+                              cudaStream_t st);
+int launch_features_bwd_transpose(const dn_csr* gt, const float* U, int rotations, int64_t V, int C,
+                                  float* dxd /*V x C*/, float* dpq /*V x 2C*/, cudaStream_t st);
+int launch_deinterleave_vc2(const float* vc2, int64_t V, int C, float* g01 /*V x 2C*/, cudaStream_t st);
+int launch_complex_dots_tanh(const float* g01, const float* b01, int64_t V, int C, float* out, cudaStream_t st);
+int launch_spectral_bwd(const float* gs_partial, int P, const float* evals, const float* time,
+                        const float* x_spec, int K, int C, float* dS /*K x C*/, float* grad_time /*+=*/,
+                        cudaStream_t st);
+
+// ---- tcgen05 engine (dn_tc.cu) ----
+bool tc_supported_device();
+// Fused chain of up to DN_MAX_LAYERS layers over 128-row tiles; layer 0 reads `src`.
+int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers, int n_layers, int64_t V, int passes /*3 or 1*/,
+                  void* ws, int64_t ws_bytes, cudaStream_t st);
+int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers);
+// partial[p][k][c] for p < *P_out
+int tc_to_basis_partial(const float* values, const float* basis, const float* massvec, int64_t V, int K, int C,
+                        float* partial, int* P_out, int passes, cudaStream_t st);
+int tc_to_basis_supported(int K, int C);
+int64_t tc_chain_ws_bytes(const DnLayer* layers, int n_layers);

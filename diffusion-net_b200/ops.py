@@ -1,0 +1,374 @@
+"""Host glue between torch tensors and the C-ABI kernels: operator prep (COO -> shared-pattern
+CSR, cached on tensor identity), workspace, and the autograd Functions of the hot path.
+
+PyTorch is plumbing only here (device memory, streams, autograd graph); every arithmetic step
+of the path runs in the hand-written kernels behind ``include/diffusion_net_b200.h``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import weakref
+
+import torch
+
+from . import _lib
+
+_ENGINES = {"simt": _lib.ENGINE_SIMT, "tc3x": _lib.ENGINE_TC3X, "tc1x": _lib.ENGINE_TC1X}
+_engine = _ENGINES[os.environ.get("DN_B200_ENGINE", "tc3x")]
+
+
+def set_engine(name: str):
+    """'tc3x' (default: tcgen05, error-compensated 3xTF32, fp32-grade), 'tc1x' (single-pass
+    TF32) or 'simt' (exact fp32 FFMA).  Shapes outside the tcgen05 kernels' envelope always
+    run the exact SIMT kernels."""
+    global _engine
+    _engine = _ENGINES[name]
+
+
+def get_engine() -> str:
+    return {v: k for k, v in _ENGINES.items()}[_engine]
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("diffusion_net_b200 runs on CUDA tensors only (there is no CPU fallback); "
+                               "got a tensor on {}".format(t.device))
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise RuntimeError("diffusion_net_b200 computes in float32; got {}".format(t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_workspaces = {}
+
+
+def workspace(V, K, C_, device):
+    need = _lib.load().dn_workspace_bytes(int(V), int(K), int(C_))
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+class GradOperators:
+    """Shared-pattern CSR of (gradX, gradY) for one mesh, plus (lazily) its transpose."""
+
+    def __init__(self, gradX, gradY):
+        _require_cuda(gradX, gradY)
+        gx = gradX if gradX.is_coalesced() else gradX.coalesce()
+        gy = gradY if gradY.is_coalesced() else gradY.coalesce()
+        if gx.dim() != 2 or gx.shape[0] != gx.shape[1] or gx.shape != gy.shape:
+            raise ValueError("gradX/gradY must be square sparse matrices of equal shape")
+        self.V = int(gx.shape[0])
+        ix, iy = gx.indices(), gy.indices()
+        if ix.shape == iy.shape and torch.equal(ix, iy):
+            idx, vx, vy = ix, gx.values(), gy.values()
+        else:  # general case: union pattern (index plumbing only)
+            z = torch.zeros_like
+            both = torch.sparse_coo_tensor(
+                torch.cat((ix, iy), dim=1),
+                torch.cat((torch.stack((gx.values(), z(gx.values())), -1),
+                           torch.stack((z(gy.values()), gy.values()), -1)), dim=0),
+                (self.V, self.V, 2)).coalesce()
+            idx, vx, vy = both.indices(), both.values()[:, 0].contiguous(), both.values()[:, 1].contiguous()
+        self.device = gx.device
+        self._coo = (idx[0].contiguous(), idx[1].contiguous(), _f32c(vx), _f32c(vy))
+        self.nnz = int(idx.shape[1])
+        self.csr = self._build(*self._coo)
+        self._csr_t = None
+
+    def _build(self, rows, cols, vx, vy):
+        lib = _lib.load()
+        rowptr = torch.empty(self.V + 1, dtype=torch.int32, device=self.device)
+        colidx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=self.device)
+        vals = torch.empty(2 * max(self.nnz, 1), dtype=torch.float32, device=self.device)
+        _lib.check(lib.dn_csr_from_coo(rows.data_ptr(), cols.data_ptr(), vx.data_ptr(), vy.data_ptr(),
+                                       self.nnz, self.V, rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(),
+                                       _stream()), "dn_csr_from_coo")
+        st = _lib.dn_csr(rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(), self.nnz)
+        return (st, rowptr, colidx, vals)   # keep the tensors alive next to the struct
+
+    @property
+    def csr_t(self):
+        """CSR of the transposed pattern (backward pass); index sort is prep-time plumbing."""
+        if self._csr_t is None:
+            rows, cols, vx, vy = self._coo
+            order = torch.argsort(cols * self.V + rows)
+            self._csr_t = self._build(cols[order].contiguous(), rows[order].contiguous(),
+                                      vx[order].contiguous(), vy[order].contiguous())
+        return self._csr_t
+
+
+_prep_cache = {}
+
+
+def prepare_operators(gradX, gradY):
+    """Memoised on the identity (+ version) of the user's sparse tensors: the reference reuses the
+    same operator tensors across blocks and epochs (SURVEY.md section 8b 'Ownership')."""
+    key = (id(gradX), id(gradY))
+    hit = _prep_cache.get(key)
+    if hit is not None:
+        rx, ry, ver, ops = hit
+        if rx() is gradX and ry() is gradY and ver == (gradX._version, gradY._version):
+            return ops
+    ops = GradOperators(gradX, gradY)
+    if len(_prep_cache) > 256:
+        for k in [k for k, v in _prep_cache.items() if v[0]() is None or v[1]() is None]:
+            del _prep_cache[k]
+        if len(_prep_cache) > 256:
+            _prep_cache.clear()
+    _prep_cache[key] = (weakref.ref(gradX), weakref.ref(gradY), (gradX._version, gradY._version), ops)
+    return ops
+
+
+def prepare_operators_batched(gradX, gradY):
+    """For the reference's stacked (B,V,V) sparse operators: one GradOperators per mesh."""
+    key = (id(gradX), id(gradY), "batched")
+    hit = _prep_cache.get(key)
+    if hit is not None:
+        rx, ry, ver, ops = hit
+        if rx() is gradX and ry() is gradY and ver == (gradX._version, gradY._version):
+            return ops
+    ops = [GradOperators(gradX[b], gradY[b]) for b in range(gradX.shape[0])]
+    _prep_cache[key] = (weakref.ref(gradX), weakref.ref(gradY), (gradX._version, gradY._version), ops)
+    return ops
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers (no autograd)
+# ------------------------------------------------------------------------------------------------
+def to_basis_raw(values, basis, massvec):
+    _require_cuda(values, basis, massvec)
+    values, basis = _f32c(values), _f32c(basis)
+    V, K = basis.shape
+    Cc = values.shape[-1]
+    out = torch.empty(K, Cc, dtype=torch.float32, device=values.device)
+    ws = workspace(V, K, Cc, values.device)
+    _lib.check(_lib.load().dn_to_basis(values.data_ptr(), basis.data_ptr(),
+                                       _f32c(massvec).data_ptr() if massvec is not None else None, V, K, Cc,
+                                       out.data_ptr(), ws.data_ptr(), ws.numel(), _engine, _stream()), "dn_to_basis")
+    return out
+
+
+def from_basis_raw(values, basis):
+    _require_cuda(values, basis)
+    values, basis = _f32c(values), _f32c(basis)
+    V, K = basis.shape
+    Cc = values.shape[-1]
+    out = torch.empty(V, Cc, dtype=torch.float32, device=values.device)
+    ws = workspace(V, K, Cc, values.device)
+    _lib.check(_lib.load().dn_from_basis(values.data_ptr(), basis.data_ptr(), None, V, K, Cc, out.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), _engine, _stream()), "dn_from_basis")
+    return out
+
+
+def grad_spmm_raw(ops: GradOperators, x):
+    x = _f32c(x)
+    V, Cc = x.shape
+    out = torch.empty(V, Cc, 2, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().dn_grad_spmm(C.byref(ops.csr[0]), x.data_ptr(), V, Cc, out.data_ptr(), _stream()),
+               "dn_grad_spmm")
+    return out
+
+
+def spatial_gradient_features_raw(vectors, A_re, A_im):
+    vectors = _f32c(vectors)
+    V, Cc, _ = vectors.shape
+    out = torch.empty(V, Cc, dtype=torch.float32, device=vectors.device)
+    ws = workspace(V, Cc, Cc, vectors.device)
+    _lib.check(_lib.load().dn_spatial_gradient_features_fwd(
+        vectors.data_ptr(), _f32c(A_re).data_ptr(), _f32c(A_im).data_ptr() if A_im is not None else None,
+        1 if A_im is not None else 0, V, Cc, out.data_ptr(), ws.data_ptr(), ws.numel(), _engine, _stream()),
+        "dn_spatial_gradient_features_fwd")
+    return out
+
+
+def block_forward_raw(x_in, mass, evals, evecs, ops, time, A_re, A_im, weights, biases, with_features):
+    """Fused inference forward of one block on one mesh (dn_block_fwd)."""
+    lib = _lib.load()
+    x_in, mass, evals, evecs = _f32c(x_in), _f32c(mass), _f32c(evals), _f32c(evecs)
+    V, Cc = x_in.shape
+    K = evecs.shape[1]
+    out = torch.empty_like(x_in)
+    ws = workspace(V, K, Cc, x_in.device)
+    dims = [weights[0].shape[1]] + [w.shape[0] for w in weights]
+    wp = _lib.ptr_array([_f32c(w).data_ptr() for w in weights])
+    bp = _lib.ptr_array([_f32c(b).data_ptr() if b is not None else None for b in biases])
+    dm = _lib.int_array(dims)
+    prm = _lib.dn_block_params(
+        time.data_ptr(), A_re.data_ptr() if A_re is not None else None,
+        A_im.data_ptr() if A_im is not None else None, 1 if with_features else 0,
+        1 if A_im is not None else 0, len(weights), wp, bp, dm)
+    csr = C.byref(ops.csr[0]) if ops is not None else None
+    _lib.check(lib.dn_block_fwd(x_in.data_ptr(), mass.data_ptr(), evals.data_ptr(), evecs.data_ptr(), csr,
+                                C.byref(prm), V, K, Cc, out.data_ptr(), ws.data_ptr(), ws.numel(), _engine,
+                                _stream()), "dn_block_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd Functions (one mesh each; gradients only w.r.t. features and parameters -- the operator
+# tuple is data)
+# ------------------------------------------------------------------------------------------------
+class DiffusionFn(torch.autograd.Function):
+    """layers.py:44-67 spectral LearnedTimeDiffusion on one mesh."""
+
+    @staticmethod
+    def forward(ctx, x, time, mass, evals, evecs):
+        lib = _lib.load()
+        x, mass, evals, evecs = _f32c(x), _f32c(mass), _f32c(evals), _f32c(evecs)
+        V, Cc = x.shape
+        K = evecs.shape[1]
+        xd = torch.empty_like(x)
+        x_spec = torch.empty(K, Cc, dtype=torch.float32, device=x.device)
+        ws = workspace(V, K, Cc, x.device)
+        # the kernel clamps `time` in place, as the reference does on the Parameter (layers.py:48-49)
+        _lib.check(lib.dn_learned_time_diffusion_fwd(x.data_ptr(), mass.data_ptr(), evals.data_ptr(),
+                                                     evecs.data_ptr(), time.data_ptr(), V, K, Cc, xd.data_ptr(),
+                                                     x_spec.data_ptr(), ws.data_ptr(), ws.numel(), _engine,
+                                                     _stream()), "dn_learned_time_diffusion_fwd")
+        ctx.save_for_backward(mass, evals, evecs, time.detach().clone(), x_spec)
+        return xd
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        mass, evals, evecs, time, x_spec = ctx.saved_tensors
+        g = _f32c(g)
+        V, Cc = g.shape
+        K = evecs.shape[1]
+        gx = torch.empty_like(g)
+        gt = torch.zeros_like(time)
+        ws = workspace(V, K, Cc, g.device)
+        _lib.check(lib.dn_learned_time_diffusion_bwd(g.data_ptr(), mass.data_ptr(), evals.data_ptr(),
+                                                     evecs.data_ptr(), time.data_ptr(), x_spec.data_ptr(), V, K, Cc,
+                                                     gx.data_ptr(), gt.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                     _engine, _stream()), "dn_learned_time_diffusion_bwd")
+        return gx, gt, None, None, None
+
+
+class GradFeaturesFn(torch.autograd.Function):
+    """layers.py:216-226: sparse tangent gradient + SpatialGradientFeatures, fused."""
+
+    @staticmethod
+    def forward(ctx, xd, A_re, A_im, ops):
+        lib = _lib.load()
+        xd, A_re = _f32c(xd), _f32c(A_re)
+        A_im = _f32c(A_im) if A_im is not None else None
+        V, Cc = xd.shape
+        rot = A_im is not None
+        feat = torch.empty_like(xd)
+        pq = torch.empty(V, (2 if rot else 1) * Cc, dtype=torch.float32, device=xd.device)
+        ws = workspace(V, Cc, Cc, xd.device)
+        _lib.check(lib.dn_gradient_features_fwd(C.byref(ops.csr[0]), xd.data_ptr(), A_re.data_ptr(),
+                                                A_im.data_ptr() if rot else None, 1 if rot else 0, V, Cc,
+                                                feat.data_ptr(), pq.data_ptr(), ws.data_ptr(), ws.numel(), _engine,
+                                                _stream()), "dn_gradient_features_fwd")
+        ctx.ops = ops
+        ctx.rot = rot
+        ctx.save_for_backward(xd, pq, feat, A_re, A_im if rot else A_re)
+        return feat
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        xd, pq, feat, A_re, A_im = ctx.saved_tensors
+        ops, rot = ctx.ops, ctx.rot
+        g = _f32c(g)
+        V, Cc = xd.shape
+        gx = torch.empty_like(xd)
+        gAre = torch.zeros_like(A_re)
+        gAim = torch.zeros_like(A_im) if rot else None
+        ws = workspace(V, Cc, Cc, xd.device)
+        _lib.check(lib.dn_gradient_features_bwd(
+            C.byref(ops.csr[0]), C.byref(ops.csr_t[0]), g.data_ptr(), xd.data_ptr(), pq.data_ptr(), feat.data_ptr(),
+            A_re.data_ptr(), A_im.data_ptr() if rot else None, 1 if rot else 0, V, Cc, gx.data_ptr(),
+            gAre.data_ptr(), gAim.data_ptr() if rot else None, ws.data_ptr(), ws.numel(), _engine, _stream()),
+            "dn_gradient_features_bwd")
+        return gx, gAre, gAim, None
+
+
+class MLPFn(torch.autograd.Function):
+    """cat(srcs) -> [Linear, ReLU, (Dropout)]* -> Linear (+ residual): layers.py:133-164, 229-239.
+
+    Call as ``MLPFn.apply(n_src, n_layers, has_residual, drop_p, *srcs, *weights, *biases[, residual])``
+    (a bias slot may be None)."""
+
+    @staticmethod
+    def forward(ctx, n_src, n_layers, has_res, drop_p, *t):
+        lib = _lib.load()
+        srcs = [_f32c(s) for s in t[:n_src]]
+        weights = [_f32c(w) for w in t[n_src:n_src + n_layers]]
+        biases = [(_f32c(b) if b is not None else None) for b in t[n_src + n_layers:n_src + 2 * n_layers]]
+        residual = _f32c(t[n_src + 2 * n_layers]) if has_res else None
+        V = srcs[0].shape[0]
+        dev = srcs[0].device
+        dims = [sum(s.shape[1] for s in srcs)] + [w.shape[0] for w in weights]
+        for l, w in enumerate(weights):
+            if w.shape[1] != dims[l]:
+                raise ValueError("MiniMLP layer {} expects {} inputs, got {}".format(l, w.shape[1], dims[l]))
+        need_grad = any(ctx.needs_input_grad)
+        hidden = [torch.empty(V, dims[l + 1], dtype=torch.float32, device=dev) for l in range(n_layers - 1)] \
+            if need_grad else []
+        masks = []
+        if drop_p > 0.0:
+            # mask generation is RNG plumbing; applying it is fused into the layer epilogue
+            masks = [torch.empty(V, dims[l + 1], dtype=torch.float32, device=dev).bernoulli_(1.0 - drop_p)
+                     .mul_(1.0 / (1.0 - drop_p)) for l in range(n_layers - 1)]
+        out = torch.empty(V, dims[-1], dtype=torch.float32, device=dev)
+        ws = workspace(V, max(dims[1:]), max(max(dims[1:]), (max(dims) + 2) // 3), dev)
+        _lib.check(lib.dn_mini_mlp_fwd(
+            _lib.ptr_array([s.data_ptr() for s in srcs]), _lib.int_array([s.shape[1] for s in srcs]), n_src,
+            _lib.ptr_array([w.data_ptr() for w in weights]),
+            _lib.ptr_array([b.data_ptr() if b is not None else None for b in biases]), _lib.int_array(dims),
+            n_layers, _lib.ptr_array([m.data_ptr() for m in masks]) if masks else None,
+            residual.data_ptr() if residual is not None else None, V,
+            _lib.ptr_array([h.data_ptr() for h in hidden]) if hidden else None, out.data_ptr(), ws.data_ptr(),
+            ws.numel(), _engine, _stream()), "dn_mini_mlp_fwd")
+        ctx.meta = (n_src, n_layers, has_res, dims, [b is not None for b in biases])
+        ctx.save_for_backward(*srcs, *weights, *hidden, *masks)
+        ctx.n_hidden, ctx.n_masks = len(hidden), len(masks)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        n_src, n_layers, has_res, dims, has_bias = ctx.meta
+        sv = ctx.saved_tensors
+        srcs = sv[:n_src]
+        weights = sv[n_src:n_src + n_layers]
+        hidden = sv[n_src + n_layers:n_src + n_layers + ctx.n_hidden]
+        masks = sv[n_src + n_layers + ctx.n_hidden:]
+        g = _f32c(g)
+        V = g.shape[0]
+        dev = g.device
+        gs = [torch.empty_like(s) for s in srcs]
+        gw = [torch.zeros_like(w) for w in weights]
+        gb = [torch.zeros(w.shape[0], dtype=torch.float32, device=dev) if hb else None
+              for w, hb in zip(weights, has_bias)]
+        ws = workspace(V, max(dims[1:]), max(max(dims[1:]), (max(dims) + 2) // 3), dev)
+        _lib.check(lib.dn_mini_mlp_bwd(
+            g.data_ptr(), _lib.ptr_array([s.data_ptr() for s in srcs]),
+            _lib.int_array([s.shape[1] for s in srcs]), n_src, _lib.ptr_array([w.data_ptr() for w in weights]),
+            _lib.int_array(dims), n_layers, _lib.ptr_array([h.data_ptr() for h in hidden]) if hidden else None,
+            _lib.ptr_array([m.data_ptr() for m in masks]) if masks else None, V,
+            _lib.ptr_array([x.data_ptr() for x in gs]), _lib.ptr_array([x.data_ptr() for x in gw]),
+            _lib.ptr_array([x.data_ptr() if x is not None else None for x in gb]), ws.data_ptr(), ws.numel(),
+            _engine, _stream()), "dn_mini_mlp_bwd")
+        res = (g,) if has_res else ()
+        return (None, None, None, None, *gs, *gw, *gb, *res)
+
+
+def mlp_apply(srcs, weights, biases, residual=None, drop_p=0.0):
+    args = list(srcs) + list(weights) + list(biases) + ([residual] if residual is not None else [])
+    return MLPFn.apply(len(srcs), len(weights), residual is not None, float(drop_p), *args)

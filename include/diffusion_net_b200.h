@@ -1,0 +1,171 @@
+/*
+ * diffusion_net_b200 -- C ABI of the B200-native DiffusionNetBlock hot path.
+ *
+ * The reference (nmwsharp/diffusion-net) is pure Python and has no FFI layer; its
+ * boundary is the module API of src/diffusion_net/layers.py plus the operator
+ * tuple of geometry.get_operators.  Each entry point below
+ * replaces one reference function on that path and is what a reference-side ctypes
+ * binding would call (INTEGRATION.md shows the stub).  Conventions:
+ *
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless a
+ *     name ends in _host; all float data is fp32, row-major, densely packed unless
+ *     a leading dimension is given;
+ *   - the caller allocates every output and the workspace (dn_workspace_bytes);
+ *   - kernels are enqueued on `stream` (a cudaStream_t) and never synchronise;
+ *   - return 0 on success, <0 for a DN_ERR_* argument/support error, >0 for a
+ *     cudaError_t raised at launch; dn_error_string() explains either;
+ *   - no global mutable state: calls on different streams are independent.
+ *
+ * `engine` selects the arithmetic of the dense contractions:
+ *   DN_ENGINE_SIMT  exact fp32 FFMA (debug / gold-on-device, any shape)
+ *   DN_ENGINE_TC3X  tcgen05 tensor cores, error-compensated 3xTF32 (fp32-grade,
+ *                   the default product path; <=1e-5 relative vs the reference)
+ *   DN_ENGINE_TC1X  tcgen05 single-pass TF32 (fast, ~5e-4 relative)
+ */
+#ifndef DIFFUSION_NET_B200_H
+#define DIFFUSION_NET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DN_ABI_VERSION 1
+
+typedef void* dn_stream_t; /* cudaStream_t */
+
+enum dn_status {
+  DN_OK = 0,
+  DN_ERR_INVALID_ARGUMENT = -1, /* null pointer, negative size, mismatched dims   */
+  DN_ERR_UNSUPPORTED = -2,      /* shape/engine combination not implemented        */
+  DN_ERR_WORKSPACE = -3,        /* workspace too small (see dn_workspace_bytes)    */
+  DN_ERR_NOT_SM100 = -4         /* tensor-core engine requested on a non-sm_100 GPU */
+};
+
+enum dn_engine { DN_ENGINE_SIMT = 0, DN_ENGINE_TC3X = 1, DN_ENGINE_TC1X = 2 };
+
+/* Shared-pattern CSR form of the (gradX, gradY) pair.  The reference hands over two
+ * coalesced COO tensors with identical, row-sorted sparsity (Re/Im of one complex
+ * matrix, geometry.py:381-382; utils.py:50-55).  vals holds (gx, gy) interleaved. */
+typedef struct dn_csr {
+  const int32_t* rowptr; /* V+1 */
+  const int32_t* colidx; /* nnz */
+  const float* vals;     /* 2*nnz: gx0, gy0, gx1, gy1, ... */
+  int64_t nnz;
+} dn_csr;
+
+/* Parameters of one DiffusionNetBlock, named as in the reference state_dict
+ * (layers.py:38, 110-113, 150-155).  nn.Linear layout: weight[n_out][n_in]. */
+typedef struct dn_block_params {
+  float* diffusion_time;     /* (C)   in/out: overwritten with max(t, 1e-8), layers.py:48-49 */
+  const float* A_re;         /* (C,C) gradient_features.A_re.weight, or .A.weight when !rotations */
+  const float* A_im;         /* (C,C) gradient_features.A_im.weight, NULL when !rotations        */
+  int with_gradient_features;
+  int with_gradient_rotations;
+  int n_mlp_layers;          /* number of Linear layers in the MiniMLP (reference default 3)      */
+  const float* const* mlp_weight_host; /* host array [n_mlp_layers] of device pointers            */
+  const float* const* mlp_bias_host;   /* host array [n_mlp_layers] of device pointers            */
+  const int* mlp_dims_host;  /* host array [n_mlp_layers+1]: 3C (or 2C), hidden..., C             */
+} dn_block_params;
+
+int dn_abi_version(void);
+const char* dn_error_string(int code);
+/* sm count / compute capability (major*10+minor) / opt-in shared memory per block of `device`. */
+int dn_device_query(int device, int* sm_count, int* cc, int64_t* smem_optin_bytes);
+
+/* Bytes of scratch any call below needs for (V, K, C); 256-byte aligned base required. */
+int64_t dn_workspace_bytes(int64_t V, int K, int C);
+
+/* Operator prep: row-sorted COO (int64 rows/cols as in utils.py:55) -> dn_csr arrays.
+ * vy may be NULL (single matrix; gy written as 0). */
+int dn_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* vx, const float* vy,
+                    int64_t nnz, int64_t V, int32_t* rowptr, int32_t* colidx, float* vals,
+                    dn_stream_t stream);
+
+/* geometry.py:572-583 to_basis: out(K,C) = basis(V,K)^T @ (values(V,C) * massvec(V)[:,None]).
+ * massvec may be NULL (no weighting; used by the backward pass). */
+int dn_to_basis(const float* values, const float* basis, const float* massvec, int64_t V, int K,
+                int C, float* out, void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream);
+
+/* geometry.py:586-598 from_basis (real branch): out(V,C) = basis(V,K) @ values(K,C).
+ * row_scale (V) optional: out rows multiplied by it (mass, backward pass). */
+int dn_from_basis(const float* values, const float* basis, const float* row_scale, int64_t V, int K,
+                  int C, float* out, void* workspace, int64_t ws_bytes, int engine,
+                  dn_stream_t stream);
+
+/* layers.py:44-67 LearnedTimeDiffusion.forward, method='spectral'.
+ * time (C) is clamped in place (layers.py:48-49).  x_spec_out (K,C) optional: the
+ * un-scaled spectral coefficients, saved for the backward pass. */
+int dn_learned_time_diffusion_fwd(const float* x, const float* mass, const float* evals,
+                                  const float* evecs, float* time, int64_t V, int K, int C,
+                                  float* x_diffuse, float* x_spec_out, void* workspace,
+                                  int64_t ws_bytes, int engine, dn_stream_t stream);
+
+/* Backward of the above w.r.t. x and time (mass/evals/evecs are data).
+ * grad_time (C) is ACCUMULATED into (+=).  */
+int dn_learned_time_diffusion_bwd(const float* grad_out, const float* mass, const float* evals,
+                                  const float* evecs, const float* time, const float* x_spec,
+                                  int64_t V, int K, int C, float* grad_x, float* grad_time,
+                                  void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream);
+
+/* layers.py:216-223: out(V,C,2) with out[v,c,0] = (gradX @ x)[v,c], out[v,c,1] = (gradY @ x)[v,c]. */
+int dn_grad_spmm(const dn_csr* grad, const float* x, int64_t V, int C, float* out,
+                 dn_stream_t stream);
+
+/* layers.py:117-130 SpatialGradientFeatures.forward on vectors(V,C,2) -> out(V,C). */
+int dn_spatial_gradient_features_fwd(const float* vectors, const float* A_re, const float* A_im,
+                                     int with_gradient_rotations, int64_t V, int C, float* out,
+                                     void* workspace, int64_t ws_bytes, int engine,
+                                     dn_stream_t stream);
+
+/* layers.py:216-226 fused: features(V,C) = SpatialGradientFeatures(stack(gradX@x, gradY@x)).
+ * The dense maps are applied before the sparse gradient (P = x A_re^T, Q = x A_im^T; the two
+ * operators commute by linearity), so the (V,C,2) tensor is never materialised.
+ * pq_out (V,2C) optional: P|Q saved for the backward pass (workspace used if NULL). */
+int dn_gradient_features_fwd(const dn_csr* grad, const float* x_diffuse, const float* A_re,
+                             const float* A_im, int with_gradient_rotations, int64_t V, int C,
+                             float* features, float* pq_out, void* workspace, int64_t ws_bytes,
+                             int engine, dn_stream_t stream);
+
+/* Backward of dn_gradient_features_fwd.  grad_t is the CSR of the TRANSPOSED pattern
+ * (same (gx,gy) values permuted).  grad_x is written; grad_A_re / grad_A_im are ACCUMULATED. */
+int dn_gradient_features_bwd(const dn_csr* grad, const dn_csr* grad_t, const float* grad_features,
+                             const float* x_diffuse, const float* pq, const float* features,
+                             const float* A_re, const float* A_im, int with_gradient_rotations,
+                             int64_t V, int C, float* grad_x, float* grad_A_re, float* grad_A_im,
+                             void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream);
+
+/* Generic fused affine chain over vertex rows (MiniMLP layers.py:133-164, first_lin/last_lin
+ * layers.py:366,373, and the block's cat+MLP+skip layers.py:229-239):
+ *   h_0 = concat_s src[s](V, width[s]);  h_{l+1} = act_l(h_l @ W_l^T + b_l) (* dropmask_l);
+ *   out = h_L (+ residual).
+ * ReLU after every layer but the last.  hidden_out[l] (optional, l < L-1) receives h_{l+1}
+ * (post-activation, post-mask) for the backward pass; drop_mask[l] (optional) is a (V, dims[l+1])
+ * multiplier applied after the activation (training-mode Dropout(p=.5), layers.py:143-147). */
+int dn_mini_mlp_fwd(const float* const* src_host, const int* src_width_host, int nsrc,
+                    const float* const* weight_host, const float* const* bias_host,
+                    const int* dims_host, int n_layers, const float* const* drop_mask_host,
+                    const float* residual, int64_t V, float* const* hidden_out_host, float* out,
+                    void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream);
+
+/* Backward of dn_mini_mlp_fwd.  hidden[l] = h_{l+1} saved by the forward.  grad_src[s] written
+ * (residual gradient is NOT added here); grad_weight / grad_bias ACCUMULATED. */
+int dn_mini_mlp_bwd(const float* grad_out, const float* const* src_host, const int* src_width_host,
+                    int nsrc, const float* const* weight_host, const int* dims_host, int n_layers,
+                    const float* const* hidden_host, const float* const* drop_mask_host, int64_t V,
+                    float* const* grad_src_host, float* const* grad_weight_host,
+                    float* const* grad_bias_host, void* workspace, int64_t ws_bytes, int engine,
+                    dn_stream_t stream);
+
+/* layers.py:200-241 DiffusionNetBlock.forward for one mesh (eval mode: no dropout, nothing
+ * saved).  L is unused by the spectral method and is not passed. */
+int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const float* evecs,
+                 const dn_csr* grad, const dn_block_params* params, int64_t V, int K, int C,
+                 float* out, void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFUSION_NET_B200_H */

@@ -75,6 +75,16 @@ def run_block(dn, C, params, x, ops, **kw):
                 res["x_grad_features_" + tag] = feats.numpy()
             res["out_" + tag] = out[0].numpy()
             res["time_after_" + tag] = blk.diffusion.diffusion_time.detach().numpy().copy()
+        if tag == "f64":
+            # gradients of loss = sum(out * R) through the reference's own autograd (fp64 gold)
+            R = torch.randn(x.shape, generator=torch.Generator().manual_seed(21), dtype=torch.float64)
+            xg = x.to(dt).unsqueeze(0).clone().requires_grad_(True)
+            out = blk(xg, cast(mass), None, cast(evals), cast(evecs), cast(gradX), cast(gradY))
+            (out[0] * R).sum().backward()
+            res["loss_R"] = R.numpy()
+            res["g:x_in"] = xg.grad[0].numpy()
+            for n, prm in blk.named_parameters():
+                res["g:" + n] = prm.grad.numpy()
     return res
 
 

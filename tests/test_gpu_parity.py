@@ -1,0 +1,290 @@
+"""Parity of the CUDA path (through the C-ABI) with the fp64 gold of the unmodified reference
+(tests/golden, written by oracle/make_golden.py) and with the numpy oracle on seeded inputs.
+
+Tolerance: north_star asks for 1e-5 relative fp32; the metric is max|ours - gold| / max|gold|
+(SURVEY.md section 8c).  TOL below is that bound; the exact-fp32 SIMT engine is held to 2e-6.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, golden_params, ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import dn_oracle as O  # noqa: E402  (checker only)
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"tc3x": 1e-5, "simt": 3e-6}
+ENGINES = ["simt", "tc3x"]
+
+
+@pytest.fixture(scope="module")
+def dn():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import diffusion_net_b200 as d
+    d._lib.load()
+    return d
+
+
+def dev(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).cuda()
+
+
+def sparse_pair(fx, prefix=""):
+    V = fx[prefix + "mass"].shape[0]
+    idx = torch.from_numpy(np.stack((fx[prefix + "g_rows"], fx[prefix + "g_cols"])).astype(np.int64))
+    gx = torch.sparse_coo_tensor(idx, torch.from_numpy(fx[prefix + "gx_vals"]), (V, V)).coalesce().cuda()
+    gy = torch.sparse_coo_tensor(idx, torch.from_numpy(fx[prefix + "gy_vals"]), (V, V)).coalesce().cuda()
+    return gx, gy
+
+
+def oracle_ops(fx, prefix=""):
+    V = fx[prefix + "mass"].shape[0]
+    r, c = fx[prefix + "g_rows"].astype(np.int64), fx[prefix + "g_cols"].astype(np.int64)
+    f = np.float64
+    return (fx[prefix + "mass"].astype(f), fx[prefix + "evals"].astype(f), fx[prefix + "evecs"].astype(f),
+            O.coo_to_csr(r, c, fx[prefix + "gx_vals"].astype(f), (V, V)),
+            O.coo_to_csr(r, c, fx[prefix + "gy_vals"].astype(f), (V, V)))
+
+
+def make_block(dn, C, params, **kw):
+    blk = dn.DiffusionNetBlock(C_width=C, mlp_hidden_dims=[C, C], dropout=False, **kw)
+    blk.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in params.items()}, strict=True)
+    return blk.cuda().eval()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name,kw", [("block_small", {}), ("block_norot", {"with_gradient_rotations": False}),
+                                     ("block_nograd", {"with_gradient_features": False})])
+def test_block_forward_golden(dn, engine, name, kw):
+    dn.set_engine(engine)
+    base = load_golden("block_small")
+    fx = load_golden(name)
+    C = fx["x_in"].shape[1]
+    blk = make_block(dn, C, golden_params(fx), **kw)
+    gx, gy = sparse_pair(base)
+    b = lambda a: dev(a).unsqueeze(0)
+    with torch.no_grad():
+        out = blk(b(fx["x_in"]), b(base["mass"]), None, b(base["evals"]), b(base["evecs"]),
+                  gx.unsqueeze(0), gy.unsqueeze(0))
+    assert out.shape == (1,) + fx["x_in"].shape
+    assert O.rel_err(out[0].cpu().numpy(), fx["out_f64"]) < TOL[engine]
+    # in-place clamp side effect on the Parameter (layers.py:48-49)
+    np.testing.assert_array_equal(blk.diffusion.diffusion_time.detach().cpu().numpy(), fx["time_after_f32"])
+    assert isinstance(blk.diffusion.diffusion_time, torch.nn.Parameter)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_block_k128_golden(dn, engine):
+    dn.set_engine(engine)
+    fx = load_golden("block_k128")
+    blk = make_block(dn, 128, golden_params(fx))
+    gx, gy = sparse_pair(fx)
+    b = lambda a: dev(a).unsqueeze(0)
+    with torch.no_grad():
+        xd = blk.diffusion(b(fx["x_in"]), None, b(fx["mass"]), b(fx["evals"]), b(fx["evecs"]))
+        out = blk(b(fx["x_in"]), b(fx["mass"]), None, b(fx["evals"]), b(fx["evecs"]), gx.unsqueeze(0),
+                  gy.unsqueeze(0))
+    assert O.rel_err(xd[0].cpu().numpy(), fx["x_diffuse_f64_as32"]) < TOL[engine]
+    assert O.rel_err(out[0].cpu().numpy(), fx["out_f64_as32"]) < TOL[engine]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_components_vs_oracle(dn, engine):
+    """to_basis / from_basis / grad spmm / SpatialGradientFeatures / MiniMLP, each through its C-ABI call."""
+    dn.set_engine(engine)
+    fx = load_golden("block_small")
+    p = golden_params(fx, np.float64)
+    mass, evals, evecs, gX, gY = oracle_ops(fx)
+    x64 = fx["x_in"].astype(np.float64)
+    x = dev(fx["x_in"])
+    spec = dn.to_basis(x, dev(fx["evecs"]), dev(fx["mass"]))
+    assert O.rel_err(spec.cpu().numpy(), O.to_basis(x64, evecs, mass)) < TOL[engine]
+    back = dn.from_basis(spec, dev(fx["evecs"]))
+    assert O.rel_err(back.cpu().numpy(), O.from_basis(spec.double().cpu().numpy(), evecs)) < TOL[engine]
+    # batched signatures
+    specb = dn.to_basis(x.unsqueeze(0), dev(fx["evecs"]).unsqueeze(0), dev(fx["mass"]).unsqueeze(0))
+    assert specb.shape == (1,) + spec.shape
+    gx, gy = sparse_pair(fx)
+    gops = dn.prepare_operators(gx, gy)
+    xd = dev(fx["x_diffuse_f32"])
+    vc2 = dn.ops.grad_spmm_raw(gops, xd)
+    ref_vc2 = O.grad_spmm(gX, gY, fx["x_diffuse_f32"].astype(np.float64))
+    assert O.rel_err(vc2.cpu().numpy(), ref_vc2) < TOL[engine]
+    sgf = dn.SpatialGradientFeatures(32).cuda()
+    sgf.load_state_dict({"A_re.weight": torch.from_numpy(fx["p:gradient_features.A_re.weight"]),
+                         "A_im.weight": torch.from_numpy(fx["p:gradient_features.A_im.weight"])})
+    with torch.no_grad():
+        f = sgf(vc2)
+    ref_f = O.spatial_gradient_features(vc2.double().cpu().numpy(), A_re=p["gradient_features.A_re.weight"],
+                                        A_im=p["gradient_features.A_im.weight"])
+    assert O.rel_err(f.cpu().numpy(), ref_f) < TOL[engine]
+    mlp = dn.MiniMLP([96, 32, 32, 32]).cuda()
+    mlp.load_state_dict({k[len("mlp."):]: torch.from_numpy(v) for k, v in golden_params(fx).items()
+                         if k.startswith("mlp.")})
+    comb = np.concatenate((fx["x_in"], fx["x_diffuse_f32"], fx["x_grad_features_f32"]), axis=-1)
+    with torch.no_grad():
+        y = mlp(dev(comb))
+    ws = [p["mlp.miniMLP_mlp_layer_{:03d}.weight".format(i)] for i in range(3)]
+    bs = [p["mlp.miniMLP_mlp_layer_{:03d}.bias".format(i)] for i in range(3)]
+    assert O.rel_err(y.cpu().numpy(), O.mini_mlp(comb.astype(np.float64), ws, bs)) < TOL[engine]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("mode", ["vertices", "edges", "faces", "global_mean"])
+def test_net_golden(dn, engine, mode):
+    dn.set_engine(engine)
+    fx = load_golden("net_small")
+    net = dn.DiffusionNet(C_in=3, C_out=8, C_width=32, N_block=2, dropout=False, outputs_at=mode)
+    net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in golden_params(fx).items()}, strict=True)
+    net = net.cuda().eval()
+    gx, gy = sparse_pair(fx, "m0_")
+    with torch.no_grad():
+        out = net(dev(fx["verts0"]), dev(fx["m0_mass"]), L=None, evals=dev(fx["m0_evals"]),
+                  evecs=dev(fx["m0_evecs"]), gradX=gx, gradY=gy,
+                  edges=dev(fx["edges"], torch.int64), faces=dev(fx["faces"], torch.int64))
+    gold = fx["out_{}_f64".format(mode)]
+    assert out.shape == gold.shape
+    assert O.rel_err(out.cpu().numpy(), gold) < TOL[engine] * 3   # 2 blocks + 2 linears deep
+
+
+def test_net_batched_sparse(dn):
+    """The reference's stacked (B,V,V) sparse operators (B=2) equal per-mesh results."""
+    dn.set_engine("tc3x")
+    fx = load_golden("net_small")
+    net = dn.DiffusionNet(C_in=3, C_out=8, C_width=32, N_block=2, dropout=False)
+    net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in golden_params(fx).items()}, strict=True)
+    net = net.cuda().eval()
+    g0x, g0y = sparse_pair(fx, "m0_")
+    g1x, g1y = sparse_pair(fx, "m1_")
+    st = lambda a, b: torch.stack((dev(fx[a]), dev(fx[b])), 0)
+    with torch.no_grad():
+        out = net(st("verts0", "verts1"), st("m0_mass", "m1_mass"), L=None, evals=st("m0_evals", "m1_evals"),
+                  evecs=st("m0_evecs", "m1_evecs"), gradX=torch.stack((g0x, g1x), 0),
+                  gradY=torch.stack((g0y, g1y), 0))
+    assert O.rel_err(out.cpu().numpy(), fx["out_batch2_f64"]) < 3e-5
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name,kw", [("block_small", {}), ("block_norot", {"with_gradient_rotations": False}),
+                                     ("block_nograd", {"with_gradient_features": False})])
+def test_block_backward_golden(dn, engine, name, kw):
+    """Gradients of sum(out*R) w.r.t. x_in and every parameter vs the reference's own autograd (fp64)."""
+    dn.set_engine(engine)
+    base = load_golden("block_small")
+    fx = load_golden(name)
+    C = fx["x_in"].shape[1]
+    blk = make_block(dn, C, golden_params(fx), **kw).train()   # dropout=False => train == eval numerics
+    gx, gy = sparse_pair(base)
+    b = lambda a: dev(a).unsqueeze(0)
+    x = b(fx["x_in"]).requires_grad_(True)
+    out = blk(x, b(base["mass"]), None, b(base["evals"]), b(base["evecs"]), gx.unsqueeze(0), gy.unsqueeze(0))
+    assert O.rel_err(out[0].detach().cpu().numpy(), fx["out_f64"]) < TOL[engine]
+    (out[0] * dev(fx["loss_R"])).sum().backward()
+    assert O.rel_err(x.grad[0].cpu().numpy(), fx["g:x_in"]) < 2e-5
+    for n, prm in blk.named_parameters():
+        assert prm.grad is not None, n
+        assert O.rel_err(prm.grad.cpu().numpy(), fx["g:" + n]) < 5e-5, n
+
+
+def test_errors_and_no_cpu_fallback(dn):
+    blk = dn.DiffusionNetBlock(C_width=32, mlp_hidden_dims=[32, 32], dropout=False)
+    x = torch.zeros(1, 10, 32)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        blk(x, torch.ones(1, 10), None, torch.zeros(1, 4), torch.zeros(1, 10, 4), None, None)
+    with pytest.raises(ValueError, match="wrong shape"):
+        blk.cuda()(torch.zeros(1, 10, 5).cuda(), torch.ones(1, 10).cuda(), None, torch.zeros(1, 4).cuda(),
+                   torch.zeros(1, 10, 4).cuda(), None, None)
+    with pytest.raises(ValueError):
+        dn.DiffusionNet(3, 4, outputs_at="nowhere")
+    with pytest.raises(ValueError, match="C_in=3"):
+        dn.DiffusionNet(3, 4, C_width=32).cuda()(torch.zeros(10, 4).cuda(), torch.ones(10).cuda())
+
+
+def _structural_case(dn, n, m, K, C, seed=0, **kw):
+    ops_t = dn.synthetic.structural_operators(n, m, K, seed=seed, device="cuda", **kw)
+    params = dn.synthetic.block_weights(C, seed=seed)
+    x = torch.randn(n * m, C, generator=torch.Generator().manual_seed(seed)).cuda()
+    return ops_t, params, x
+
+
+def _oracle_block(ops_t, params, x):
+    mass, L, evals, evecs, gradX, gradY = ops_t
+    gxc, gyc = gradX.coalesce().cpu(), gradY.coalesce().cpu()
+    V = mass.shape[0]
+    f = np.float64
+    gX = O.coo_to_csr(gxc.indices()[0].numpy(), gxc.indices()[1].numpy(), gxc.values().numpy().astype(f), (V, V))
+    gY = O.coo_to_csr(gyc.indices()[0].numpy(), gyc.indices()[1].numpy(), gyc.values().numpy().astype(f), (V, V))
+    p64 = {k: v.numpy().astype(f) for k, v in params.items()}
+    return O.diffusion_net_block(x.cpu().numpy().astype(f), mass.cpu().numpy().astype(f),
+                                 evals.cpu().numpy().astype(f), evecs.cpu().numpy().astype(f), gX, gY, p64)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("n,m,K,C,kw", [
+    (40, 50, 64, 32, {}),                 # BASELINE config 1 shape (V=2000,K=64,C=32)
+    (5, 10, 8, 16, {}),                   # V=50 < one row tile
+    (23, 31, 40, 64, {"permute": True}),  # ragged V, K not a power of two, scattered gathers
+    (20, 25, 128, 256, {}),               # C_width=256 (BASELINE config 3 width)
+    (70, 100, 128, 128, {}),              # human-seg shape (config 2)
+])
+def test_block_vs_oracle_shapes(dn, engine, n, m, K, C, kw):
+    dn.set_engine(engine)
+    ops_t, params, x = _structural_case(dn, n, m, K, C, **kw)
+    mass, L, evals, evecs, gradX, gradY = ops_t
+    blk = make_block(dn, C, {k: v.numpy() for k, v in params.items()})
+    with torch.no_grad():
+        out = blk(x.unsqueeze(0), mass.unsqueeze(0), None, evals.unsqueeze(0), evecs.unsqueeze(0), [gradX], [gradY])
+    gold = _oracle_block(ops_t, params, x)
+    assert O.rel_err(out[0].cpu().numpy(), gold) < TOL[engine]
+
+
+def test_empty_rows_and_union_pattern(dn):
+    """A vertex with no gradient entries, and gradX/gradY with different sparsity patterns."""
+    dn.set_engine("tc3x")
+    V, C = 64, 16
+    g = torch.Generator().manual_seed(5)
+    rows = torch.randint(1, V, (300,), generator=g)       # row 0 stays empty
+    cols = torch.randint(0, V, (300,), generator=g)
+    gx = torch.sparse_coo_tensor(torch.stack((rows, cols)), torch.randn(300, generator=g), (V, V)).coalesce().cuda()
+    rows2 = torch.randint(1, V, (200,), generator=g)
+    cols2 = torch.randint(0, V, (200,), generator=g)
+    gy = torch.sparse_coo_tensor(torch.stack((rows2, cols2)), torch.randn(200, generator=g), (V, V)).coalesce().cuda()
+    gops = dn.prepare_operators(gx, gy)
+    x = torch.randn(V, C, generator=g).cuda()
+    out = dn.ops.grad_spmm_raw(gops, x)
+    ref = torch.stack((torch.sparse.mm(gx, x), torch.sparse.mm(gy, x)), -1)
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
+    assert torch.all(out[0] == 0)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_full_size_properties(dn, engine):
+    """BASELINE metric size (V=200k,K=128,C=128): oracle check plus size-independent properties."""
+    dn.set_engine(engine)
+    n, m, K, C = 400, 500, 128, 128
+    ops_t, params, x = _structural_case(dn, n, m, K, C, seed=1)
+    mass, L, evals, evecs, gradX, gradY = ops_t
+    blk = make_block(dn, C, {k: v.numpy() for k, v in params.items()})
+    b = lambda t: t.unsqueeze(0)
+    with torch.no_grad():
+        out = blk(b(x), b(mass), None, b(evals), b(evecs), [gradX], [gradY])
+        # linearity of the spectral diffusion in x
+        x2 = torch.randn_like(x)
+        d = lambda t: blk.diffusion(b(t), None, b(mass), b(evals), b(evecs))[0]
+        lhs = d(2.0 * x + 3.0 * x2)
+        rhs = 2.0 * d(x) + 3.0 * d(x2)
+        assert O.rel_err(lhs.cpu().numpy(), rhs.cpu().numpy()) < 2e-5
+        # t -> 0: diffusion is the M-orthogonal projection onto span(evecs), hence idempotent
+        blk.diffusion.diffusion_time.data.fill_(0.0)
+        p1 = d(x)
+        p2 = d(p1)
+        assert float(blk.diffusion.diffusion_time.min()) == pytest.approx(1e-8)
+        assert O.rel_err(p2.cpu().numpy(), p1.cpu().numpy()) < 2e-5
+    gold = _oracle_block(ops_t, params, x)
+    assert O.rel_err(out[0].cpu().numpy(), gold) < TOL[engine]

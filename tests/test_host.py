@@ -1,0 +1,143 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol the header declares;
+the module mirror keeps the reference's names/keys/errors; host-side sharding and the gradient
+all-reduce (gloo, world_size 2).  No GPU compute here."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT, GOLDEN
+
+import diffusion_net_b200 as dn
+
+
+def test_library_builds_and_exports_header_symbols():
+    dn._lib.build()
+    lib = dn._lib.load()
+    hdr = open(os.path.join(ROOT, "include", "diffusion_net_b200.h")).read()
+    declared = set(re.findall(r"\b(dn_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(dn._lib.SIGNATURES), declared ^ set(dn._lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.dn_abi_version() == 1
+    assert lib.dn_error_string(-3).decode().startswith("diffusion_net_b200: workspace")
+    assert lib.dn_workspace_bytes(200000, 128, 128) > 0
+    assert lib.dn_workspace_bytes(-1, 128, 128) == -1
+
+
+def test_sass_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", dn._lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_state_dict_keys_match_shipped_checkpoints():
+    man = json.load(open(os.path.join(GOLDEN, "statedict_manifest.json")))
+    assert man
+    for name, keys in man.items():
+        # the functional-map checkpoints wrap the net as `feature_extractor.` (fmaps_model.py)
+        pre = "feature_extractor."
+        if all(k.startswith(pre) for k in keys):
+            keys = {k[len(pre):]: v for k, v in keys.items()}
+        C_in = keys["first_lin.weight"][1]
+        C_out = keys["last_lin.weight"][0]
+        C_width = keys["first_lin.weight"][0]
+        n_block = len([k for k in keys if k.endswith("diffusion.diffusion_time")])
+        net = dn.DiffusionNet(C_in=C_in, C_out=C_out, C_width=C_width, N_block=n_block)
+        ours = {k: list(v.shape) for k, v in net.state_dict().items()}
+        assert ours == keys, name
+
+
+def test_live_checkpoint_strict_load():
+    path = "/root/reference/experiments/human_segmentation_original/pretrained_models/human_seg_xyz_4x128.pth"
+    if not os.path.exists(path):
+        pytest.skip("reference checkpoints only exist in the build container")
+    sd = torch.load(path, map_location="cpu", weights_only=True)
+    net = dn.DiffusionNet(C_in=3, C_out=8, C_width=128, N_block=4, outputs_at="faces")
+    net.load_state_dict(sd, strict=True)
+    assert len(net.blocks) == 4 and net.blocks[0] is net.block_0
+
+
+def test_variant_keys_and_module_layout():
+    b = dn.DiffusionNetBlock(16, [16, 16], with_gradient_rotations=False)
+    assert "gradient_features.A.weight" in b.state_dict()
+    b2 = dn.DiffusionNetBlock(16, [16, 16], with_gradient_features=False)
+    assert b2.state_dict()["mlp.miniMLP_mlp_layer_000.weight"].shape == (16, 32)
+    kinds = [type(m).__name__ for m in dn.MiniMLP([48, 16, 16, 16], dropout=True)]
+    assert kinds == ["Linear", "ReLU", "Dropout", "Linear", "ReLU", "Dropout", "Linear"]
+    assert float(dn.LearnedTimeDiffusion(8).diffusion_time.abs().sum()) == 0.0
+
+
+def test_errors_match_reference():
+    with pytest.raises(ValueError, match="invalid setting for outputs_at"):
+        dn.DiffusionNet(3, 4, outputs_at="bad")
+    with pytest.raises(ValueError, match="invalid setting for diffusion_method"):
+        dn.DiffusionNet(3, 4, diffusion_method="bad")
+    net = dn.DiffusionNet(3, 4, C_width=16, N_block=1)
+    with pytest.raises(ValueError, match="C_in=3"):
+        net(torch.zeros(10, 5), torch.ones(10))
+    with pytest.raises(ValueError, match="shape"):
+        net(torch.zeros(2, 2, 10, 3), torch.ones(10))
+    blk = dn.DiffusionNetBlock(16, [16, 16])
+    with pytest.raises(ValueError, match="wrong shape"):
+        blk(torch.zeros(1, 10, 5), None, None, None, None, None, None)
+    # no CPU fallback: the product path refuses CPU tensors loudly
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        blk(torch.zeros(1, 10, 16), torch.ones(1, 10), None, torch.zeros(1, 4), torch.zeros(1, 10, 4), None, None)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "diffusion-net_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_shard_meshes_lpt():
+    from diffusion_net_b200.dist import shard_meshes, mesh_cost
+    costs = [mesh_cost(1800 + 50 * (i % 9), 128, 128) for i in range(32)]
+    for ws in (1, 2, 4, 8):
+        shards = shard_meshes(costs, ws)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(32))
+        loads = [sum(costs[i] for i in s) for s in shards]
+        assert max(loads) <= min(loads) * 1.1 + 1
+    assert shard_meshes([5, 1, 1, 1], 2) == [[0], [1, 2, 3]]
+
+
+def test_allreduce_gradients_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from diffusion_net_b200.dist import allreduce_gradients, shard_meshes
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(0)
+lin = torch.nn.Linear(4, 3)
+frozen = torch.nn.Parameter(torch.ones(2), requires_grad=False)
+for p in lin.parameters():
+    p.grad = torch.full_like(p, float(r + 1))
+allreduce_gradients(list(lin.parameters()) + [frozen], n_global_meshes=4)
+exp = sum(range(1, w + 1)) / 4.0
+assert all(torch.allclose(p.grad, torch.full_like(p, exp)) for p in lin.parameters())
+assert frozen.grad is None
+mine = shard_meshes([3.0, 2.0, 2.0, 1.0], w)[r]
+got = [None] * w
+dist.all_gather_object(got, mine)
+assert sorted(i for s in got for i in s) == [0, 1, 2, 3]
+dist.barrier()
+if r == 0: print("GLOO_OK")
+''' % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout + r.stderr
