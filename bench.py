@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""DiffusionNetBlock forward throughput (BASELINE.json metric): Mverts/s at V=200k, K=128, C=128.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3            # our arm (one JSON line on rank 0)
+    python bench.py --impl reference --steps 5 --warmup 1      # the reference's CPU path (torch-CPU port)
+    torchrun ... bench.py --gpus N ...                         # one rank per GPU, one mesh per rank (weak scaling)
+
+A "step" is one DiffusionNetBlock forward (eval, no_grad, fp32) over one synthetic mesh per GPU:
+Tier-S operators on a 400x500 torus (V=200000, 7 nnz/row, M-orthonormal random eigenbasis, K=128),
+C_width=128, seeded weights.  `value` has all inputs resident in HBM; `e2e`
+goes through the public module API from pinned HOST buffers (H2D of features + the whole operator
+tuple, CSR prep, forward, D2H of the result inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TORUS, M_TORUS, K_EIG, C_WIDTH = 400, 500, 128, 128
+NNZ_ROW = 7
+METRIC = "DiffusionNetBlock forward Mverts/sec at V=200k,K=128,C=128; 1/2/4/8 GPU"
+
+
+def flops_per_vertex(K, C, r=NNZ_ROW):
+    return 4 * K * C + 18 * C * C + 4 * r * C           # SURVEY.md 8d (reference op count)
+
+
+def bytes_per_vertex(K, C, r=NNZ_ROW, s=4):
+    return s * (5 * C + 2 * K) + 12 * r + 8             # SURVEY.md 8d (minimum HBM traffic)
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            m = json.load(fh)
+        p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (profiling recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        if not sm:
+            return None
+        mx = max(float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower() == "active"
+                                                          for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+def make_workload(dn, device, seed):
+    import torch
+    ops_t = dn.synthetic.structural_operators(N_TORUS, M_TORUS, K_EIG, seed=seed, device="cpu")
+    params = dn.synthetic.block_weights(C_WIDTH, seed=seed)
+    x = torch.randn(N_TORUS * M_TORUS, C_WIDTH, generator=torch.Generator().manual_seed(100 + seed))
+    return ops_t, params, x
+
+
+def cpu_port_step(T, host, params):
+    import torch
+    mass, L, evals, evecs, gradX, gradY, x = host
+    with torch.no_grad():
+        # stacked (B,V,V) sparse operators indexed per mesh, as DiffusionNet.forward hands them over
+        return T.block_forward(x.unsqueeze(0), mass.unsqueeze(0), evals.unsqueeze(0), evecs.unsqueeze(0),
+                               gradX.unsqueeze(0), gradY.unsqueeze(0), params)
+
+
+def time_cpu_port(host, params, steps, warmup):
+    """The reference's own CPU PyTorch path (oracle/dn_oracle_torch.py port) on all host threads."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dn_oracle_torch as T   # the timed CPU arm; never on the product path
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(warmup):
+        cpu_port_step(T, host, params)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_port_step(T, host, params)
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return ts[len(ts) // 2], cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import diffusion_net_b200 as dn
+    V = N_TORUS * M_TORUS
+    (mass, L, evals, evecs, gradX, gradY), params, x = make_workload(dn, "cpu", 0)
+    steps, warm = max(1, args.steps), max(1, args.warmup)
+    sec, cores = time_cpu_port((mass, L, evals, evecs, gradX, gradY, x), params, steps, warm)
+    val = V / sec / 1e6
+    sample = "full workload: 1 mesh V={} K={} C={}, {} steps (median), {} warm-up".format(V, K_EIG, C_WIDTH, steps, warm)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mverts/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "block_fwd V=200000 K=128 C=128 (1 mesh, host CPU)", "device": "cpu"},
+        "cpu_baseline": {"value": val, "unit": "Mverts/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mverts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default=os.environ.get("DN_B200_ENGINE", "tc3x"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    args = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import diffusion_net_b200 as dn
+
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = dn._lib.load()
+    dn.set_engine(args.engine)
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    V = N_TORUS * M_TORUS
+
+    host_ops, params, x_host = make_workload(dn, "cpu", rank)
+    mass, L, evals, evecs, gradX, gradY = [t.to(dev) for t in host_ops]
+    x = x_host.to(dev)
+    blk = dn.DiffusionNetBlock(C_width=C_WIDTH, mlp_hidden_dims=[C_WIDTH, C_WIDTH], dropout=False)
+    blk.load_state_dict(params, strict=True)
+    blk = blk.to(dev).eval()
+    xb, mb, eb, vb = x.unsqueeze(0), mass.unsqueeze(0), evals.unsqueeze(0), evecs.unsqueeze(0)
+
+    def step():
+        with torch.no_grad():
+            return blk(xb, mb, None, eb, vb, [gradX], [gradY])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.dn_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        out = step()
+    ev1.record()
+    barrier()
+    launches = lib.dn_kernel_launch_count() - l0
+    ms_total = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_total.item()) / steps
+    clocks = sampler.stop()
+    value = world * V / (ms_step * 1e-3) / 1e6
+
+    # ---- end to end through the public API from pinned host buffers ----
+    pin = lambda t: t.contiguous().pin_memory()
+    gxc, gyc = host_ops[4].coalesce(), host_ops[5].coalesce()
+    h = {"x": pin(x_host), "mass": pin(host_ops[0]), "evals": pin(host_ops[2]), "evecs": pin(host_ops[3]),
+         "gi": pin(gxc.indices()), "gxv": pin(gxc.values()), "gyv": pin(gyc.values())}
+    out_host = torch.empty(V, C_WIDTH).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in h.values())
+    d2h = out_host.numel() * 4
+
+    def e2e_step():
+        d = {k: t.to(dev, non_blocking=True) for k, t in h.items()}
+        gx = torch.sparse_coo_tensor(d["gi"], d["gxv"], (V, V), is_coalesced=True)
+        gy = torch.sparse_coo_tensor(d["gi"], d["gyv"], (V, V), is_coalesced=True)
+        with torch.no_grad():
+            o = blk(d["x"].unsqueeze(0), d["mass"].unsqueeze(0), None, d["evals"].unsqueeze(0),
+                    d["evecs"].unsqueeze(0), [gx], [gy])
+        out_host.copy_(o[0], non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = world * V / (float(e2e_ms.item()) / args.e2e_steps * 1e-3) / 1e6
+
+    # ---- per-stage device times (rank 0): which kernel dominates, and its roofline ----
+    roof, stages = None, None
+    if rank == 0:
+        pk = peaks()
+        gops = dn.prepare_operators(gradX, gradY)
+        A_re, A_im = blk.gradient_features.weights()
+        lins = blk.mlp.linears()
+        xd = torch.empty_like(x)
+        feat = torch.empty_like(x)
+
+        def t_ms(fn, n=10):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+
+        with torch.no_grad():
+            st_to = t_ms(lambda: dn.ops.to_basis_raw(x, evecs, mass))
+            st_diff = t_ms(lambda: dn.ops.DiffusionFn.apply(x, blk.diffusion.diffusion_time, mass, evals, evecs))
+            xd = dn.ops.DiffusionFn.apply(x, blk.diffusion.diffusion_time, mass, evals, evecs)
+            st_gf = t_ms(lambda: dn.ops.GradFeaturesFn.apply(xd, A_re, A_im, gops))
+            feat = dn.ops.GradFeaturesFn.apply(xd, A_re, A_im, gops)
+            st_mlp = t_ms(lambda: dn.ops.mlp_apply([x, xd, feat], [l.weight for l in lins], [l.bias for l in lins],
+                                                   residual=x))
+        stages = {"to_basis_ms": st_to, "diffusion_ms": st_diff, "grad_features_ms": st_gf, "mlp_ms": st_mlp}
+        # dominant kernel: the fused MiniMLP chain (rows_chain_kernel); algorithmic work per vertex:
+        #   flops 10 C^2 (3C->C->C->C), bytes 4*(3C + C) (read x_in,x_diffuse,features; write out)
+        C = C_WIDTH
+        mlp_flops, mlp_bytes = 10 * C * C * V, 4 * 4 * C * V
+        tf = mlp_flops / (st_mlp * 1e-3) / 1e12
+        gbs = mlp_bytes / (st_mlp * 1e-3) / 1e9
+        t_tensor_min = mlp_flops / (pk["bf16_tflops"] * 1e12)
+        t_hbm_min = mlp_bytes / (pk["hbm_gbs"] * 1e9)
+        if t_tensor_min >= t_hbm_min:
+            roof = {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": tf / pk["bf16_tflops"], "traffic": None}
+        else:
+            roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": gbs / pk["hbm_gbs"], "traffic": None}
+        roof.update({"kernel": "rows_chain_kernel (MiniMLP+skip)", "ms": st_mlp, "peak_source": pk["source"],
+                     "issued_flop_factor": 3 if args.engine == "tc3x" else 1,
+                     "note": "useful fp32-equivalent flops vs measured bf16 cuBLAS burst peak; tf32 MMAs run at "
+                             "half the bf16 rate and 3xTF32 issues 3 MMAs per product",
+                     "block_hbm_frac": bytes_per_vertex(K_EIG, C) * V / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"]})
+
+    # ---- the reference's CPU path beside it (rank 0, N=1 only; bounded sample) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, cores = time_cpu_port((host_ops[0], host_ops[1], host_ops[2], host_ops[3], host_ops[4], host_ops[5],
+                                    x_host), params, 3, 1)
+        cpu = {"value": V / sec / 1e6, "unit": "Mverts/s", "cores": cores, "kind": "port",
+               "sample": "same workload (1 mesh V=200000), 3 steps median, 1 warm-up, torch-CPU port of the "
+                         "reference block forward"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "Mverts/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "block_fwd V=200000 K=128 C=128, 1 mesh per GPU", "engine": args.engine,
+                       "parallelism": "mesh-sharded x{}".format(world), "l2": "inputs (~330 MB/step) exceed the 126 MB L2",
+                       "gflop_per_step": flops_per_vertex(K_EIG, C_WIDTH) * V / 1e9,
+                       "min_hbm_mb_per_step": bytes_per_vertex(K_EIG, C_WIDTH) * V / 1e6},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_val, "unit": "Mverts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": args.e2e_steps},
+            "roofline": roof, "stages_ms": stages, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

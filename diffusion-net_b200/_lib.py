@@ -65,6 +65,7 @@ SIGNATURES = {
     "dn_abi_version": (_I, []),
     "dn_error_string": (C.c_char_p, [_I]),
     "dn_device_query": (_I, [_I, _IP, _IP, C.POINTER(_L)]),
+    "dn_kernel_launch_count": (_L, []),
     "dn_workspace_bytes": (_L, [_L, _I, _I]),
     "dn_csr_from_coo": (_I, [_P, _P, _P, _P, _L, _L, _P, _P, _P, _P]),
     "dn_to_basis": (_I, [_P, _P, _P, _L, _I, _I, _P, _P, _L, _I, _P]),

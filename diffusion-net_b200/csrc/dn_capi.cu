@@ -77,9 +77,13 @@ int to_basis_partials(const float* values, const float* basis, const float* mass
 
 }  // namespace
 
+long long g_dn_launches = 0;
+
 extern "C" {
 
 int dn_abi_version(void) { return DN_ABI_VERSION; }
+
+int64_t dn_kernel_launch_count(void) { return (int64_t)g_dn_launches; }
 
 const char* dn_error_string(int code) {
   switch (code) {

@@ -15,10 +15,13 @@
     if (_e != cudaSuccess) return (int)_e;         \
   } while (0)
 
+extern long long g_dn_launches;   // kernels launched by this library (reported by bench.py)
+
 #define DN_LAUNCH_CHECK()                          \
   do {                                             \
     cudaError_t _e = cudaGetLastError();           \
     if (_e != cudaSuccess) return (int)_e;         \
+    ++g_dn_launches;                               \
   } while (0)
 
 // One affine layer applied to 128-row tiles of vertices:  out = epi(A @ W^T + bias)

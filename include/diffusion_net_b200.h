@@ -75,6 +75,10 @@ const char* dn_error_string(int code);
 /* sm count / compute capability (major*10+minor) / opt-in shared memory per block of `device`. */
 int dn_device_query(int device, int* sm_count, int* cc, int64_t* smem_optin_bytes);
 
+/* Number of kernels this library has launched so far in this process (monotonic; bench.py
+ * differences it around the timed region). */
+int64_t dn_kernel_launch_count(void);
+
 /* Bytes of scratch any call below needs for (V, K, C); 256-byte aligned base required. */
 int64_t dn_workspace_bytes(int64_t V, int K, int C);
 

@@ -81,3 +81,21 @@ def test_wrong_channels_raises():
     mass, evals, evecs, gX, gY = ops_of(fx, np.float32)
     with pytest.raises(ValueError):
         O.diffusion_net_block(fx["x_in"][:, :5], mass, evals, evecs, gX, gY, golden_params(fx))
+
+
+def test_torch_port_matches_reference():
+    """The torch-CPU port timed by bench.py reproduces the live-reference outputs."""
+    import torch
+    import dn_oracle_torch as T
+    for name, kw in (("block_small", {}), ("block_norot", {}), ("block_nograd", {"with_gradient_features": False})):
+        base = load_golden("block_small")
+        fx = load_golden(name)
+        V = base["mass"].shape[0]
+        idx = torch.from_numpy(np.stack((base["g_rows"], base["g_cols"])).astype(np.int64))
+        gX = torch.sparse_coo_tensor(idx, torch.from_numpy(base["gx_vals"]), (V, V)).coalesce()
+        gY = torch.sparse_coo_tensor(idx, torch.from_numpy(base["gy_vals"]), (V, V)).coalesce()
+        p = {k: torch.from_numpy(v) for k, v in golden_params(fx).items()}
+        b = lambda a: torch.from_numpy(a).unsqueeze(0)
+        out = T.block_forward(b(fx["x_in"]), b(base["mass"]), b(base["evals"]), b(base["evecs"]), [gX], [gY], p, **kw)
+        assert O.rel_err(out[0].numpy(), fx["out_f32"]) < 1e-6
+        assert O.rel_err(out[0].numpy(), fx["out_f64"]) < 2e-6
