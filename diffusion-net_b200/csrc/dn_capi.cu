@@ -44,9 +44,12 @@ inline DnRowsSrc one_src(const float* p, int width, int64_t ld) {
 // `tmp0/tmp1` are V x maxN ping-pong buffers used only by the unfused SIMT route.
 int run_chain(const DnRowsSrc& src, DnLayer* layers, int n_layers, int64_t V, int engine, float* tmp0,
               float* tmp1, void* tc_ws, int64_t tc_ws_bytes, cudaStream_t st) {
-  if (use_tc(engine) && tc_supported_device() && tc_rows_chain_supported(src, layers, n_layers) == DN_OK) {
+  const bool tc = use_tc(engine) && tc_supported_device();
+  if (tc && tc_rows_chain_supported(src, layers, n_layers) == DN_OK) {
     return tc_rows_chain(src, layers, n_layers, V, tc_passes(engine), tc_ws, tc_ws_bytes, st);
   }
+  // not fusable as a whole (e.g. a 256-wide layer inside a chain): layer by layer, each on the
+  // tensor-core kernel when its shape allows, on the exact SIMT kernel otherwise
   DnRowsSrc cur = src;
   for (int l = 0; l < n_layers; ++l) {
     DnLayer L = layers[l];
@@ -58,7 +61,11 @@ int run_chain(const DnRowsSrc& src, DnLayer* layers, int n_layers, int64_t V, in
       if (!o) return DN_ERR_WORKSPACE;
     }
     L.out = o; L.ld_out = ldo;
-    int rc = simt_rows_gemm(cur, L, V, st);
+    int rc;
+    if (tc && tc_rows_chain_supported(cur, &L, 1) == DN_OK)
+      rc = tc_rows_chain(cur, &L, 1, V, tc_passes(engine), tc_ws, tc_ws_bytes, st);
+    else
+      rc = simt_rows_gemm(cur, L, V, st);
     if (rc) return rc;
     cur = one_src(o, L.N, ldo);
   }

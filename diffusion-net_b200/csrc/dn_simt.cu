@@ -266,11 +266,18 @@ __global__ void colsum_kernel(const float* __restrict__ A, int64_t lda, int N, i
 __global__ void spectral_scale_kernel(const float* __restrict__ partial, int P, const float* __restrict__ evals,
                                       float* __restrict__ time, int K, int C, float* __restrict__ x_spec_out,
                                       float* __restrict__ S_out, int clamp_writeback) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= K * C) return;
+  // block = 64 consecutive elements x 4 slices of the P partial sums (more loads in flight)
+  __shared__ float red[4][64];
+  const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  const int idx = blockIdx.x * 64 + e;
+  float acc = 0.f;
+  if (idx < K * C)
+    for (int p = sl; p < P; p += 4) acc += partial[(int64_t)p * K * C + idx];
+  red[sl][e] = acc;
+  __syncthreads();
+  if (sl != 0 || idx >= K * C) return;
   const int k = idx / C, c = idx % C;
-  float s = 0.f;
-  for (int p = 0; p < P; ++p) s += partial[(int64_t)p * K * C + idx];
+  const float s = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
   const float t = fmaxf(time[c], 1e-8f);              // torch.clamp(t, min=1e-8)
   const float coef = expf(-(evals[k] * t));           // torch.exp(-evals.unsqueeze(-1) * time.unsqueeze(0))
   if (x_spec_out) x_spec_out[idx] = s;
@@ -558,8 +565,8 @@ int simt_colsum(const float* A, int64_t lda, int N, int64_t V, float* out, int a
 
 int launch_spectral_scale(const float* partial, int P, const float* evals, float* time, int K, int C,
                           float* x_spec_out, float* S_out, int clamp_writeback, cudaStream_t st) {
-  spectral_scale_kernel<<<(K * C + 255) / 256, 256, 0, st>>>(partial, P, evals, time, K, C, x_spec_out, S_out,
-                                                              clamp_writeback);
+  spectral_scale_kernel<<<(K * C + 63) / 64, 256, 0, st>>>(partial, P, evals, time, K, C, x_spec_out, S_out,
+                                                            clamp_writeback);
   DN_LAUNCH_CHECK();
   return DN_OK;
 }

@@ -25,13 +25,13 @@ using namespace tc;
 
 constexpr int KC = 16;                          // k-elements per pipeline chunk (2 MMA k-steps of 8)
 constexpr int TILE_M = 128;                     // vertex rows per tile == UMMA M
-constexpr int NSA = 4, NSB = 4;                 // ring depths
+constexpr int NSA = 3;                          // activation-operand ring depth
 constexpr int A_IMG = TILE_M * KC * 4;          // 8 KiB: one hi (or lo) A chunk image
 constexpr int A_STAGE = 2 * A_IMG;              // hi + lo
-constexpr int B_STAGE = 2 * 256 * KC * 4;       // 32 KiB: hi + lo at N = 256
+constexpr int B_BYTES = 65536;                  // weight ring: 4 stages at N<=128, 2 stages at N=256
 constexpr int A_LBO = (TILE_M / 8) * 128;       // 2048 B between k-groups (4 elements) of A
 constexpr int CHAIN_THREADS = 320;              // warp0 TMA, warp1 MMA, warps 2..9 workers (2 warpgroups)
-constexpr int CHAIN_SMEM = NSA * A_STAGE + NSB * B_STAGE + 1024;
+constexpr int CHAIN_SMEM = NSA * A_STAGE + B_BYTES + 256;   // 114,944 B: two CTAs fit one SM
 
 struct TcLayer {
   const float* wpack;
@@ -50,13 +50,16 @@ struct TcChainParams {
   int n_layers;
   int passes;
   int variant;
+  int nmax;       // 128 or 256: widest layer (sizes the weight stages and the TMEM buffers)
+  int kch;        // K-chunk size the kernel instance uses (16 or 32)
+  int prefetch;   // sources are row-contiguous: bulk-prefetch the next tile into L2
   int64_t V;
 };
 
 // ---------------------------------------------------------------------------------------------
 // weight pack:  W -> [chunk][hi | lo][ (k/4)*N*16B + (n/8)*128B + (n%8)*16B + (k%4)*4B ]
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ W, int64_t ldw, int w_trans, int K, int N,
+__global__ void pack_weights_kernel(const float* __restrict__ W, int64_t ldw, int w_trans, int K, int N, int kc,
                                     float* __restrict__ dst) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= K * N) return;
@@ -64,8 +67,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, int64_t ldw, in
   const float w = w_trans ? W[(int64_t)k * ldw + n] : W[(int64_t)n * ldw + k];
   float hi, lo;
   split_tf32(w, hi, lo);
-  const int chunk = k / KC, kk = k % KC;
-  const int64_t img = (int64_t)N * KC;   // floats per image
+  const int chunk = k / kc, kk = k % kc;
+  const int64_t img = (int64_t)N * kc;   // floats per image
   const int64_t off = (int64_t)chunk * 2 * img + (int64_t)(kk >> 2) * (N * 4) + (n >> 3) * 32 + (n & 7) * 4 + (kk & 3);
   dst[off] = hi;
   dst[off + img] = lo;
@@ -75,37 +78,52 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, int64_t ldw, in
 // helpers shared by the worker warps
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_split4(uint8_t* a_hi, uint8_t* a_lo, uint32_t byte_off, float4 v, int passes) {
+  // hi = rna_tf32(x); lo = x - hi is exact in fp32 and the tensor core reads only its top 19 bits
   float4 h, l;
-  split_tf32(v.x, h.x, l.x);
-  split_tf32(v.y, h.y, l.y);
-  split_tf32(v.z, h.z, l.z);
-  split_tf32(v.w, h.w, l.w);
+  split_tf32_fast(v.x, h.x, l.x);
+  split_tf32_fast(v.y, h.y, l.y);
+  split_tf32_fast(v.z, h.z, l.z);
+  split_tf32_fast(v.w, h.w, l.w);
   *reinterpret_cast<float4*>(a_hi + byte_off) = h;
   if (passes == 3) *reinterpret_cast<float4*>(a_lo + byte_off) = l;
 }
 
 // ---------------------------------------------------------------------------------------------
 // fused affine chain over 128-row tiles
+//
+// Two CTAs are co-resident per SM (320 threads, <=113 KB smem, 256 TMEM columns each): while one
+// CTA sits in a layer boundary (accumulator drain -> next operand chunks) the other keeps the
+// tensor pipe busy.  Per CTA: warp 0 streams weight chunks with bulk TMA (and L2-prefetches the
+// next tile's rows), warp 1 issues the MMAs, warps 2..9 (two warpgroups, alternating K-chunks)
+// build operand chunks (from HBM/L2 for layer 0, from the TMEM accumulator for chained layers)
+// and run the epilogues.  Every role is latency-bound per chunk, so throughput comes from having
+// many chunks in flight (2 CTAs x 2 warpgroups) and from keeping the per-chunk instruction
+// streams short (incremental ring counters, descriptor templates, one cvt per split).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CHAIN_THREADS, 1) rows_chain_kernel(const __grid_constant__ TcChainParams p) {
+__global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __grid_constant__ TcChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smA = smem;
   uint8_t* smB = smem + NSA * A_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSA * A_STAGE + NSB * B_STAGE);
-  // bars: [0,NSA) a_full | [NSA,2NSA) a_empty | [2NSA, 2NSA+NSB) b_full | [.., +NSB) b_empty | d_full
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSA * A_STAGE + B_BYTES);
+  // bars: a_full[NSA] a_empty[NSA] b_full[4] b_empty[4] d_full[2] d_empty[2]
   const uint32_t a_full = smem_u32(bars), a_empty = smem_u32(bars + NSA);
-  const uint32_t b_full = smem_u32(bars + 2 * NSA), b_empty = smem_u32(bars + 2 * NSA + NSB);
-  const uint32_t d_full = smem_u32(bars + 2 * NSA + 2 * NSB);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSA + 2 * NSB + 2);
+  const uint32_t b_full = smem_u32(bars + 2 * NSA), b_empty = smem_u32(bars + 2 * NSA + 4);
+  const uint32_t d_full = smem_u32(bars + 2 * NSA + 8), d_empty = smem_u32(bars + 2 * NSA + 10);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSA + 12);
+
+  const int nmax = p.nmax;                                  // 128 or 256: widest layer
+  const uint32_t b_stage = 2u * (uint32_t)nmax * KC * 4;    // hi + lo weight chunk (16 or 32 KiB)
+  const uint32_t nsb = B_BYTES / b_stage;                   // 4 or 2 weight stages
+  const uint32_t nbuf = 256u / (uint32_t)nmax;              // 2 or 1 accumulator buffers in TMEM
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSA; ++i) { mbar_init(a_full + 8 * i, 4); mbar_init(a_empty + 8 * i, 1); }
-    for (int i = 0; i < NSB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    mbar_init(d_full, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(d_full + 8 * i, 1); mbar_init(d_empty + 8 * i, 8); }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<512>(smem_u32(tmem_slot));
+  if (warp == 0) tmem_alloc<256>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -115,121 +133,167 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) rows_chain_kernel(const __gr
   const int64_t ntiles = (p.V + TILE_M - 1) / TILE_M;
 
   if (warp == 0) {
-    // ===================== weight producer (bulk TMA) =====================
-    if (lane == 0) {
-      uint32_t ci = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-        for (int l = 0; l < L; ++l) {
-          const int N = p.layer[l].N, nch = p.layer[l].K / KC;
-          const uint32_t img_bytes = (uint32_t)N * KC * 4;
-          const uint32_t bytes = p.passes == 3 ? 2 * img_bytes : img_bytes;
-          for (int c = 0; c < nch; ++c, ++ci) {
-            const uint32_t s = ci % NSB, ph = (ci / NSB) & 1;
-            mbar_wait(b_empty + 8 * s, ph ^ 1);
-            mbar_arrive_expect_tx(b_full + 8 * s, bytes);
-            tma_bulk_g2s(smem_u32(smB + s * B_STAGE), p.layer[l].wpack + (int64_t)c * 2 * N * KC, bytes,
-                         b_full + 8 * s);
+    // ===================== weight producer (bulk TMA; warp-uniform, one elected lane issues) =====
+    uint32_t s = 0, ph = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t nt = tile + gridDim.x;
+      if (p.prefetch && nt < ntiles && elect_one()) {
+        // the next tile's 128 rows of every source are one contiguous block: pull them into L2 now
+        const int64_t r0 = nt * TILE_M;
+        const int64_t rows = (p.V - r0) < TILE_M ? (p.V - r0) : TILE_M;
+        for (int q = 0; q < p.src.nsrc; ++q)
+          l2_prefetch_bulk(p.src.ptr[q] + r0 * p.src.ld[q], (uint32_t)(rows * p.src.width[q] * 4));
+      }
+      __syncwarp();
+      for (int l = 0; l < L; ++l) {
+        const int N = p.layer[l].N, nch = p.layer[l].K / KC;
+        const uint32_t img_bytes = (uint32_t)N * KC * 4;
+        const uint32_t bytes = p.passes == 3 ? 2 * img_bytes : img_bytes;
+        const float* wsrc = p.layer[l].wpack;
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(b_empty + 8 * s, ph ^ 1);
+          if (elect_one()) {
+            if (p.variant & 32) {      // timing ablation only
+              mbar_arrive(b_full + 8 * s);
+            } else {
+              mbar_arrive_expect_tx(b_full + 8 * s, bytes);
+              tma_bulk_g2s(smem_u32(smB + s * b_stage), wsrc + (int64_t)c * 2 * N * KC, bytes, b_full + 8 * s);
+            }
           }
+          __syncwarp();
+          if (++s == nsb) { s = 0; ph ^= 1; }
         }
+      }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      uint32_t ci = 0, g = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-        for (int l = 0; l < L; ++l, ++g) {
-          const int N = p.layer[l].N, nch = p.layer[l].K / KC;
-          const uint32_t idesc = make_idesc_tf32(TILE_M, N);
-          const uint32_t d_tmem = tmem_base + (g & 1) * 256;
-          const uint32_t b_lbo = (uint32_t)N * 16, b_img = (uint32_t)N * KC * 4;
-          uint32_t lboA = A_LBO, sboA = 128, lboB = b_lbo, sboB = 128;
-          if (p.variant & 1) { lboA = 128; sboA = A_LBO; lboB = 128; sboB = b_lbo; }
-          for (int c = 0; c < nch; ++c, ++ci) {
-            const uint32_t sa = ci % NSA, pa = (ci / NSA) & 1, sb = ci % NSB, pb = (ci / NSB) & 1;
-            mbar_wait(a_full + 8 * sa, pa);
-            mbar_wait(b_full + 8 * sb, pb);
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(smA + sa * A_STAGE), a_lo = a_hi + A_IMG;
-            const uint32_t b_hi = smem_u32(smB + sb * B_STAGE), b_lo = b_hi + b_img;
+    // ===================== MMA issuer (warp-uniform loop; one elected lane issues) ==============
+    // descriptor = template (LBO | SBO | version) + (smem address >> 4); k-steps / lo images are
+    // constant increments of the address field
+    const uint64_t tmplA = (p.variant & 1) ? make_desc(0, 128, A_LBO) : make_desc(0, A_LBO, 128);
+    const uint32_t smA_u = smem_u32(smA) >> 4, smB_u = smem_u32(smB) >> 4;
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, g = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int l = 0; l < L; ++l, ++g) {
+        const int N = p.layer[l].N, nch = p.layer[l].K / KC;
+        const uint32_t idesc = make_idesc_tf32(TILE_M, N);
+        const uint32_t buf = (nbuf == 2) ? (g & 1) : 0, use = (nbuf == 2) ? (g >> 1) : g;
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)nmax;
+        const uint32_t b_lbo = (uint32_t)N * 16;
+        const uint64_t tmplB = (p.variant & 1) ? make_desc(0, 128, b_lbo) : make_desc(0, b_lbo, 128);
+        const uint32_t b_img_u = ((uint32_t)N * KC * 4) >> 4, b_ks_u = (2 * b_lbo) >> 4;
+        if (use > 0) {   // the epilogue of the previous user of this accumulator buffer must be done
+          mbar_wait(d_empty + 8 * buf, (use - 1) & 1);
+          tc_fence_after();
+        }
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(a_full + 8 * sa, pa);
+          mbar_wait(b_full + 8 * sb, pb);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t dah = tmplA + (smA_u + sa * (A_STAGE >> 4));
+            const uint64_t dbh = tmplB + (smB_u + sb * (b_stage >> 4));
 #pragma unroll
             for (int ks = 0; ks < KC / 8; ++ks) {
-              const uint32_t ao = ks * 2 * A_LBO, bo = ks * 2 * b_lbo;
-              const uint64_t dah = make_desc(a_hi + ao, lboA, sboA), dbh = make_desc(b_hi + bo, lboB, sboB);
+              const uint64_t a_h = dah + ks * ((2 * A_LBO) >> 4), b_h = dbh + ks * b_ks_u;
               const uint32_t acc = (c | ks) ? 1u : 0u;
               if (p.passes == 3) {
-                const uint64_t dal = make_desc(a_lo + ao, lboA, sboA), dbl = make_desc(b_lo + bo, lboB, sboB);
-                mma_tf32_ss(d_tmem, dal, dbh, idesc, acc);
-                mma_tf32_ss(d_tmem, dah, dbl, idesc, 1u);
-                mma_tf32_ss(d_tmem, dah, dbh, idesc, 1u);
+                if (!(p.variant & 8)) mma_tf32_ss(d_tmem, a_h + (A_IMG >> 4), b_h, idesc, acc);
+                if (!(p.variant & 8)) mma_tf32_ss(d_tmem, a_h, b_h + b_img_u, idesc, 1u);
+                if (!(p.variant & 8)) mma_tf32_ss(d_tmem, a_h, b_h, idesc, 1u);
               } else {
-                mma_tf32_ss(d_tmem, dah, dbh, idesc, acc);
+                mma_tf32_ss(d_tmem, a_h, b_h, idesc, acc);
               }
             }
             mma_commit(a_empty + 8 * sa);
             mma_commit(b_empty + 8 * sb);
+            if (c + 1 == nch) mma_commit(d_full + 8 * buf);
           }
-          mma_commit(d_full);
+          __syncwarp();
+          if (++sa == NSA) { sa = 0; pa ^= 1; }
+          if (++sb == nsb) { sb = 0; pb ^= 1; }
         }
-    }
+      }
   } else {
     // ===================== workers: A-chunk producers + epilogue =====================
-    const int wg = (warp - 2) >> 2;           // chunk parity this warpgroup owns
-    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int wg = (warp - 2) >> 2;           // K-chunk parity this warpgroup owns
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access (rows 32q..32q+31)
     const int rl = lane & 7, kg = lane >> 3;  // conversion mapping: 8 rows x 4 k-groups per warp step
     uint32_t ci = 0, g = 0;
+    const int nch0 = p.layer[0].K / KC;
+    // byte offset of this lane's 16-byte slot inside an operand image, conversion mapping
+    const uint32_t cv_off = kg * A_LBO + (4 * quarter) * 128 + rl * 16;     // + it * 128
+    auto load_chunk = [&](int64_t row0_, int c, float4* r) {
+      int k0 = c * KC, s = 0;
+      while (s + 1 < p.src.nsrc && k0 >= p.src.width[s]) { k0 -= p.src.width[s]; ++s; }
+      const int64_t ld = p.src.ld[s];
+      const float* base = p.src.ptr[s] + k0 + 4 * kg + (row0_ + 32 * quarter + rl) * ld;
+      const int64_t rem = p.V - (row0_ + 32 * quarter + rl);
+#pragma unroll
+      for (int it = 0; it < 4; ++it)
+        r[it] = (8 * it < rem && !(p.variant & 4)) ? __ldg(reinterpret_cast<const float4*>(base + 8 * it * ld))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto store_chunk = [&](uint32_t cidx, const float4* r) {
+      const uint32_t s = cidx % NSA, ph = (cidx / NSA) & 1;
+      mbar_wait(a_empty + 8 * s, ph ^ 1);
+      uint8_t* a_hi = smA + s * A_STAGE + cv_off;
+#pragma unroll
+      for (int it = 0; it < 4; ++it)
+        if (!(p.variant & 64)) store_split4(a_hi, a_hi + A_IMG, it * 128, r[it], p.passes);
+      if (!(p.variant & 2)) fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full + 8 * s);
+    };
+    float4 r[4];
+    if ((int64_t)blockIdx.x < ntiles && wg < nch0) load_chunk((int64_t)blockIdx.x * TILE_M, wg, r);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t row0 = tile * TILE_M;
       for (int l = 0; l < L; ++l, ++g) {
         const TcLayer& Lr = p.layer[l];
         const int nch = Lr.K / KC;
         if (l == 0) {
-          // ---- layer-0 operand from HBM: float4 loads -> hi/lo split -> canonical smem
-          auto load_chunk = [&](int c, float4* r) {
-            int k0 = c * KC, s = 0;
-            while (s + 1 < p.src.nsrc && k0 >= p.src.width[s]) { k0 -= p.src.width[s]; ++s; }
-            const float* base = p.src.ptr[s] + k0 + 4 * kg;
-            const int64_t ld = p.src.ld[s];
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int64_t row = row0 + 32 * quarter + 8 * it + rl;
-              r[it] = (row < p.V) ? __ldg(reinterpret_cast<const float4*>(base + row * ld))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          };
-          float4 cur[4], nxt[4];
-          if (wg < nch) load_chunk(wg, cur);
           for (int c = wg; c < nch; c += 2) {
-            if (c + 2 < nch) load_chunk(c + 2, nxt);
-            const uint32_t cidx = ci + c, s = cidx % NSA, ph = (cidx / NSA) & 1;
-            mbar_wait(a_empty + 8 * s, ph ^ 1);
-            uint8_t* a_hi = smA + s * A_STAGE;
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int r = 32 * quarter + 8 * it + rl;
-              store_split4(a_hi, a_hi + A_IMG, kg * A_LBO + (r >> 3) * 128 + (r & 7) * 16, cur[it], p.passes);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full + 8 * s);
-#pragma unroll
-            for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
+            store_chunk(ci + c, r);
+            if (c + 2 < nch) load_chunk(row0, c + 2, r);
           }
+          const int64_t nt = tile + gridDim.x;   // first chunk of the next tile: hidden behind the epilogues
+          if (nt < ntiles && wg < nch0) load_chunk(nt * TILE_M, wg, r);
         }
         const uint32_t ci_next = ci + nch;
         // ---- epilogue of layer l (and operand production for layer l+1)
-        mbar_wait(d_full, g & 1);
-        tc_fence_after();
         const bool has_next = (l + 1 < L);
         const int64_t row = row0 + 32 * quarter + lane;
-        const int r = 32 * quarter + lane;
-        const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
-        for (int c = wg; c < Lr.N / KC; c += 2) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(32 * quarter) << 16) + (g & 1) * 256 + c * KC, v);
-          const int n0 = c * KC;
-          if (Lr.bias) {
+        const int rr_ = 32 * quarter + lane;
+        const uint32_t ep_off = (rr_ >> 3) * 128 + (rr_ & 7) * 16;
+        const int nco = Lr.N / KC;
+        const bool has_res = Lr.residual != nullptr && !(p.variant & 256);
+        const uint32_t buf = (nbuf == 2) ? (g & 1) : 0, use = (nbuf == 2) ? (g >> 1) : g;
+        auto load_res = [&](int c, float4* q) {
+          const float4* rp = reinterpret_cast<const float4*>(Lr.residual + row * Lr.ld_res + c * KC);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += __ldg(Lr.bias + n0 + j);
+          for (int j = 0; j < 4; ++j) q[j] = (row < p.V) ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        float4 res[4];
+        if (has_res && wg < nco) load_res(wg, res);     // requested before waiting for the accumulator
+        const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
+        mbar_wait(d_full + 8 * buf, use & 1);
+        tc_fence_after();
+        const uint32_t d_lane = tmem_base + ((uint32_t)(32 * quarter) << 16) + buf * (uint32_t)nmax;
+        for (int c = wg; c < nco; c += 2) {
+          float v[16];
+          if (!(p.variant & 16)) tmem_ld16(d_lane + c * KC, v);
+          else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 1.f;
+          }
+          const int n0 = c * KC;
+          if (Lr.bias && !(p.variant & 256)) {
+            const float4* bp = reinterpret_cast<const float4*>(Lr.bias + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = __ldg(bp + j);
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
           }
           if (Lr.relu) {
 #pragma unroll
@@ -239,15 +303,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) rows_chain_kernel(const __gr
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] *= rs;
           }
-          if (Lr.residual && row < p.V) {
-            const float4* rp = reinterpret_cast<const float4*>(Lr.residual + row * Lr.ld_res + n0);
+          if (has_res) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 q = __ldg(rp + j);
-              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+              v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
             }
+            if (c + 2 < nco) load_res(c + 2, res);
           }
-          if (Lr.out && row < p.V) {
+          if (Lr.out && row < p.V && !(p.variant & 128)) {
             float4* op = reinterpret_cast<float4*>(Lr.out + row * Lr.ld_out + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -255,17 +318,21 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) rows_chain_kernel(const __gr
           if (has_next) {
             const uint32_t cidx = ci_next + c, s = cidx % NSA, ph = (cidx / NSA) & 1;
             mbar_wait(a_empty + 8 * s, ph ^ 1);
-            uint8_t* a_hi = smA + s * A_STAGE;
+            uint8_t* a_hi = smA + s * A_STAGE + ep_off;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              store_split4(a_hi, a_hi + A_IMG, j * A_LBO + (r >> 3) * 128 + (r & 7) * 16,
-                           make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), p.passes);
-            fence_proxy_async();
+              if (!(p.variant & 64))
+                store_split4(a_hi, a_hi + A_IMG, j * A_LBO,
+                             make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), p.passes);
+            if (!(p.variant & 2)) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full + 8 * s);
           }
         }
+        // accumulator buffer drained: hand it back to the MMA warp
         tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty + 8 * buf);
         ci = ci_next;
       }
     }
@@ -273,7 +340,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) rows_chain_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 0) tmem_dealloc<512>(tmem_base);
+  if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -287,9 +354,12 @@ constexpr int TB_SBO = 144;
 constexpr int TB_LBO = 16 * TB_SBO;          // 16 eight-row groups (128 rows) per k-group
 constexpr int TB_IMG = 4 * TB_LBO;           // 4 k-groups (16 v) : 9216 B
 constexpr int TB_STAGE = 4 * TB_IMG;         // A hi, A lo, B hi, B lo
-constexpr int TB_NS = 4;
-constexpr int TB_THREADS = 320;              // warp0 idle/alloc, warp1 MMA, warps 2..9 workers
-constexpr int TB_SMEM = TB_NS * TB_STAGE + 1024;
+constexpr int TB_NOP = 2;                    // operand (UMMA-layout) ring depth
+constexpr int TB_NST = 6;                    // raw TMA staging ring depth
+constexpr int TB_RAW_HALF = KC * 128 * 4;    // 16 rows x up to 128 floats
+constexpr int TB_RAW = 2 * TB_RAW_HALF;      // raw Phi rows + raw x rows
+constexpr int TB_THREADS = 320;              // warp0 TMA, warp1 MMA, warps 2..9 converters
+constexpr int TB_SMEM = TB_NST * TB_RAW + TB_NOP * TB_STAGE + 1024;
 
 struct TcToBasisParams {
   const float* values;   // (V, C)
@@ -301,22 +371,30 @@ struct TcToBasisParams {
   int64_t chunks_per_cta;
 };
 
+// TMEM columns: [0,128) correction terms (lo*hi + hi*lo); [128,256) [256,384) [384,512) three
+// round-robin accumulators for hi*hi.  Short, separate accumulation chains keep the truncation
+// of the tensor-core accumulator below fp32 noise even for V = 200k.
 __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_constant__ TcToBasisParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TB_NS * TB_STAGE);
-  const uint32_t full = smem_u32(bars), empty = smem_u32(bars + TB_NS), d_full = smem_u32(bars + 2 * TB_NS);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TB_NS + 2);
+  uint8_t* raw = smem;
+  uint8_t* opr = smem + TB_NST * TB_RAW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TB_NST * TB_RAW + TB_NOP * TB_STAGE);
+  const uint32_t st_full = smem_u32(bars), st_empty = smem_u32(bars + TB_NST);
+  const uint32_t op_full = smem_u32(bars + 2 * TB_NST), op_empty = smem_u32(bars + 2 * TB_NST + TB_NOP);
+  const uint32_t d_full = smem_u32(bars + 2 * TB_NST + 2 * TB_NOP);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TB_NST + 2 * TB_NOP + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TB_NS; ++i) { mbar_init(full + 8 * i, 8); mbar_init(empty + 8 * i, 1); }
+    for (int i = 0; i < TB_NST; ++i) { mbar_init(st_full + 8 * i, 1); mbar_init(st_empty + 8 * i, 8); }
+    for (int i = 0; i < TB_NOP; ++i) { mbar_init(op_full + 8 * i, 8); mbar_init(op_empty + 8 * i, 1); }
     mbar_init(d_full, 1);
     fence_barrier_init();
   }
   // operand rows that no lane writes (k >= K or c >= C inside the 128-row images) must be zero
-  for (int i = threadIdx.x; i < TB_NS * TB_STAGE / 16; i += blockDim.x)
-    reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < TB_NOP * TB_STAGE / 16; i += blockDim.x)
+    reinterpret_cast<float4*>(opr)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_proxy_async();
-  if (warp == 0) tmem_alloc<128>(smem_u32(tmem_slot));
+  if (warp == 0) tmem_alloc<512>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -328,87 +406,112 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
   if (c_end > total_chunks) c_end = total_chunks;
   const int64_t nch = c_end > c_beg ? c_end - c_beg : 0;
 
-  if (warp == 1) {
-    if (lane == 0 && nch > 0) {
-      const uint32_t idesc = make_idesc_tf32(128, p.C);
-      uint32_t lbo = TB_LBO, sbo = TB_SBO;
-      if (p.variant & 1) { lbo = TB_SBO; sbo = TB_LBO; }
-      for (int64_t c = 0; c < nch; ++c) {
-        const uint32_t s = c % TB_NS, ph = (c / TB_NS) & 1;
-        mbar_wait(full + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * TB_STAGE), a_lo = a_hi + TB_IMG, b_hi = a_hi + 2 * TB_IMG,
-                       b_lo = a_hi + 3 * TB_IMG;
+  if (warp == 0) {
+    // ===== TMA producer: 16 consecutive rows of Phi and of x are contiguous in HBM =====
+    for (int64_t c = 0; c < nch; ++c) {
+      const uint32_t s = c % TB_NST, ph = (c / TB_NST) & 1;
+      mbar_wait(st_empty + 8 * s, ph ^ 1);
+      const int64_t v0 = (c_beg + c) * KC;
+      const int nv = (int)((p.V - v0) < KC ? (p.V - v0) : KC);
+      const uint32_t ba = (uint32_t)nv * p.K * 4, bb = (uint32_t)nv * p.C * 4;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(st_full + 8 * s, ba + bb);
+        tma_bulk_g2s(smem_u32(raw + s * TB_RAW), p.basis + v0 * p.K, ba, st_full + 8 * s);
+        tma_bulk_g2s(smem_u32(raw + s * TB_RAW + TB_RAW_HALF), p.values + v0 * p.C, bb, st_full + 8 * s);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (warp-uniform loop; one elected lane issues) =====
+    const uint32_t idesc = make_idesc_tf32(128, p.C);
+    uint32_t lbo = TB_LBO, sbo = TB_SBO;
+    if (p.variant & 1) { lbo = TB_SBO; sbo = TB_LBO; }
+    for (int64_t c = 0; c < nch; ++c) {
+      const uint32_t s = c % TB_NOP, ph = (c / TB_NOP) & 1;
+      mbar_wait(op_full + 8 * s, ph);
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(opr + s * TB_STAGE), a_lo = a_hi + TB_IMG, b_hi = a_hi + 2 * TB_IMG,
+                     b_lo = a_hi + 3 * TB_IMG;
+      const uint32_t d_main = tmem_base + 128 * (1 + (uint32_t)(c % 3));
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < KC / 8; ++ks) {
           const uint32_t o = ks * 2 * TB_LBO;
           const uint64_t dah = make_desc(a_hi + o, lbo, sbo), dbh = make_desc(b_hi + o, lbo, sbo);
-          const uint32_t acc = (c | ks) ? 1u : 0u;
           if (p.passes == 3) {
             const uint64_t dal = make_desc(a_lo + o, lbo, sbo), dbl = make_desc(b_lo + o, lbo, sbo);
-            mma_tf32_ss(tmem_base, dal, dbh, idesc, acc);
+            mma_tf32_ss(tmem_base, dal, dbh, idesc, (c | ks) ? 1u : 0u);
             mma_tf32_ss(tmem_base, dah, dbl, idesc, 1u);
-            mma_tf32_ss(tmem_base, dah, dbh, idesc, 1u);
-          } else {
-            mma_tf32_ss(tmem_base, dah, dbh, idesc, acc);
           }
+          mma_tf32_ss(d_main, dah, dbh, idesc, (c >= 3 || ks) ? 1u : 0u);
         }
-        mma_commit(empty + 8 * s);
+        mma_commit(op_empty + 8 * s);
+        if (c + 1 == nch) mma_commit(d_full);
       }
-      mma_commit(d_full);
+      __syncwarp();
     }
-  } else if (warp >= 2) {
-    // warps 2..5: A = Phi^T, v-group (warp-2); warps 6..9: B = (m x)^T, v-group (warp-6)
+  } else {
+    // ===== converters: warps 2..5 build A = Phi^T, warps 6..9 build B = (m x)^T; 4 vertices each =====
     const int w = warp - 2;
     const bool isB = w >= 4;
-    const int vg = w & 3;                           // which 4 of the chunk's 16 vertices
-    const float* src = isB ? p.values : p.basis;
+    const int vg = w & 3;
     const int width = isB ? p.C : p.K;
-    const bool active = 4 * lane < width;           // this lane's 4 columns exist
-    auto load4 = [&](int64_t chunk, float4* r) {
-      const int64_t v0 = (c_beg + chunk) * KC + 4 * vg;
+    const bool active = 4 * lane < width;
+    const bool use_mass = isB && p.mass;
+    // mass values are fetched one chunk ahead so their L2/HBM latency is off the per-chunk path
+    float mnext[4] = {1.f, 1.f, 1.f, 1.f};
+    if (use_mass && nch > 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int64_t v = v0 + j;
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active && v < p.V) {
-          q = __ldg(reinterpret_cast<const float4*>(src + v * width + 4 * lane));
-          if (isB && p.mass) {
-            const float m = __ldg(p.mass + v);
-            q.x *= m; q.y *= m; q.z *= m; q.w *= m;     // (values * massvec), geometry.py:583
-          }
-        }
-        r[j] = q;
+        const int64_t v = c_beg * KC + 4 * vg + j;
+        mnext[j] = (v < p.V) ? __ldg(p.mass + v) : 0.f;
       }
-    };
-    float4 cur[4], nxt[4];
-    if (nch > 0) load4(0, cur);
+    }
     for (int64_t c = 0; c < nch; ++c) {
-      if (c + 1 < nch) load4(c + 1, nxt);
-      const uint32_t s = c % TB_NS, ph = (c / TB_NS) & 1;
-      mbar_wait(empty + 8 * s, ph ^ 1);
+      const int64_t v0 = (c_beg + c) * KC + 4 * vg;
+      float m[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[j] = mnext[j];
+      if (use_mass && c + 1 < nch) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mnext[j] = (v0 + KC + j < p.V) ? __ldg(p.mass + v0 + KC + j) : 0.f;
+      }
+      const uint32_t s = c % TB_NST, ph = (c / TB_NST) & 1;
+      mbar_wait(st_full + 8 * s, ph);
+      float4 q[4];
+      const uint8_t* rp = raw + s * TB_RAW + (isB ? TB_RAW_HALF : 0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && v0 + j < p.V)
+          q[j] = *reinterpret_cast<const float4*>(rp + (size_t)(4 * vg + j) * width * 4 + 16 * lane);
+        q[j].x *= m[j]; q[j].y *= m[j]; q[j].z *= m[j]; q[j].w *= m[j];   // (values * massvec), geometry.py:583
+      }
+      const uint32_t o = c % TB_NOP, po = (c / TB_NOP) & 1;
+      mbar_wait(op_empty + 8 * o, po ^ 1);
       if (active) {
-        uint8_t* hi = smem + s * TB_STAGE + (isB ? 2 * TB_IMG : 0);
+        uint8_t* hi = opr + o * TB_STAGE + (isB ? 2 * TB_IMG : 0);
         uint8_t* lo = hi + TB_IMG;
-        // transpose the 4(v) x 4(col) block: one 16-byte k-major vector per column
-        const float col[4][4] = {{cur[0].x, cur[1].x, cur[2].x, cur[3].x},
-                                 {cur[0].y, cur[1].y, cur[2].y, cur[3].y},
-                                 {cur[0].z, cur[1].z, cur[2].z, cur[3].z},
-                                 {cur[0].w, cur[1].w, cur[2].w, cur[3].w}};
+        // transpose the 4(v) x 4(col) block: one 16-byte k-major vector per operand row
+        const float col[4][4] = {{q[0].x, q[1].x, q[2].x, q[3].x},
+                                 {q[0].y, q[1].y, q[2].y, q[3].y},
+                                 {q[0].z, q[1].z, q[2].z, q[3].z},
+                                 {q[0].w, q[1].w, q[2].w, q[3].w}};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int m = 4 * lane + i;   // operand row (eigen-index k, or channel c)
-          store_split4(hi, lo, vg * TB_LBO + (m >> 3) * TB_SBO + (m & 7) * 16,
+          const int mrow = 4 * lane + i;   // operand row (eigen-index k, or channel c)
+          store_split4(hi, lo, vg * TB_LBO + (mrow >> 3) * TB_SBO + (mrow & 7) * 16,
                        make_float4(col[i][0], col[i][1], col[i][2], col[i][3]), p.passes);
         }
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(full + 8 * s);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+      if (lane == 0) {
+        mbar_arrive(op_full + 8 * o);
+        mbar_arrive(st_empty + 8 * s);
+      }
     }
-    // ---- epilogue: TMEM -> partial[cta][k][c]   (warps 2..5 cover the four lane quarters)
+    // ---- epilogue: sum the TMEM accumulators -> partial[cta][k][c]  (warps 2..5 = 4 lane quarters)
     if (w < 4) {
       float* out = p.partial + (int64_t)blockIdx.x * p.K * p.C;
       const int quarter = warp & 3;
@@ -417,13 +520,20 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
         mbar_wait(d_full, 0);
         tc_fence_after();
       }
+      const uint32_t lane_base = tmem_base + ((uint32_t)(32 * quarter) << 16);
       for (int c0 = 0; c0 < p.C; c0 += 16) {
         float v[16];
-        if (nch > 0) {
-          tmem_ld16(tmem_base + ((uint32_t)(32 * quarter) << 16) + c0, v);
-        } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        if (nch > 0) {
+          float t[16];
+          if (p.passes == 3) tmem_ld16(lane_base + c0, v);
+          const int nmain = nch < 3 ? (int)nch : 3;
+          for (int b = 0; b < nmain; ++b) {
+            tmem_ld16(lane_base + 128 * (1 + b) + c0, t);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += t[j];
+          }
         }
         if (k < p.K) {
           float4* op = reinterpret_cast<float4*>(out + (int64_t)k * p.C + c0);
@@ -436,7 +546,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 0) tmem_dealloc<128>(tmem_base);
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
 int g_tc_ok = -1;
@@ -461,6 +571,8 @@ bool tc_supported_device() {
       if (g_tc_ok) {
         if (cudaFuncSetAttribute(rows_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM) !=
                 cudaSuccess ||
+            cudaFuncSetAttribute(rows_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
             cudaFuncSetAttribute(to_basis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM) !=
                 cudaSuccess) {
           cudaGetLastError();
@@ -478,18 +590,21 @@ int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_l
   if (n_layers < 1 || n_layers > DN_MAX_LAYERS) return DN_ERR_UNSUPPORTED;
   int k0 = 0;
   for (int s = 0; s < src.nsrc; ++s) {
-    if (src.width[s] % KC || src.ld[s] % 4 || (reinterpret_cast<uintptr_t>(src.ptr[s]) & 15)) return DN_ERR_UNSUPPORTED;
+    if (src.width[s] % 16 || src.ld[s] % 4 || (reinterpret_cast<uintptr_t>(src.ptr[s]) & 15)) return DN_ERR_UNSUPPORTED;
     k0 += src.width[s];
   }
   if (k0 != layers[0].K) return DN_ERR_UNSUPPORTED;
   for (int l = 0; l < n_layers; ++l) {
     const DnLayer& L = layers[l];
-    if (L.K % KC || L.K < 2 * KC || L.N % 16 || L.N < 16 || L.N > 256) return DN_ERR_UNSUPPORTED;
+    if (L.K % 16 || L.K < 16 || L.N % 16 || L.N < 16 || L.N > 256) return DN_ERR_UNSUPPORTED;
     if (L.emul || L.relu_mask_src) return DN_ERR_UNSUPPORTED;
+    if (L.bias && (reinterpret_cast<uintptr_t>(L.bias) & 15)) return DN_ERR_UNSUPPORTED;
     if (L.residual && (L.res_scale != 1.f || L.ld_res % 4 || (reinterpret_cast<uintptr_t>(L.residual) & 15)))
       return DN_ERR_UNSUPPORTED;
     if (L.out && (L.ld_out % 4 || (reinterpret_cast<uintptr_t>(L.out) & 15))) return DN_ERR_UNSUPPORTED;
     if (l > 0 && L.K != layers[l - 1].N) return DN_ERR_UNSUPPORTED;
+    // a 256-wide accumulator fills this CTA's TMEM: no room to ping-pong between chained layers
+    if (L.N > 128 && n_layers > 1) return DN_ERR_UNSUPPORTED;
   }
   if (!layers[n_layers - 1].out) return DN_ERR_UNSUPPORTED;
   return DN_OK;
@@ -513,11 +628,18 @@ int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers, int n_layers, int
   p.passes = passes;
   p.variant = env_variant();
   p.V = V;
+  p.nmax = 128;
+  p.prefetch = 1;
+  for (int l = 0; l < n_layers; ++l)
+    if (layers[l].N > 128) p.nmax = 256;
+  p.kch = KC;
+  for (int s = 0; s < src.nsrc; ++s)
+    if (src.ld[s] != src.width[s]) p.prefetch = 0;
   char* wp = static_cast<char*>(ws);
   for (int l = 0; l < n_layers; ++l) {
     const DnLayer& L = layers[l];
     float* dst = reinterpret_cast<float*>(wp);
-    pack_weights_kernel<<<(L.K * L.N + 255) / 256, 256, 0, st>>>(L.W, L.ldw, L.w_trans, L.K, L.N, dst);
+    pack_weights_kernel<<<(L.K * L.N + 255) / 256, 256, 0, st>>>(L.W, L.ldw, L.w_trans, L.K, L.N, p.kch, dst);
     DN_LAUNCH_CHECK();
     TcLayer& T = p.layer[l];
     T.wpack = dst; T.bias = L.bias; T.residual = L.residual; T.ld_res = L.ld_res; T.row_scale = L.row_scale;
@@ -525,7 +647,7 @@ int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers, int n_layers, int
     wp += ((int64_t)L.K * L.N * 2 * 4 + 255) / 256 * 256;
   }
   const int64_t ntiles = (V + TILE_M - 1) / TILE_M;
-  const int grid = (int)(ntiles < g_sm_count ? ntiles : g_sm_count);
+  const int grid = (int)(ntiles < 2 * g_sm_count ? ntiles : 2 * g_sm_count);
   rows_chain_kernel<<<grid, CHAIN_THREADS, CHAIN_SMEM, st>>>(p);
   DN_LAUNCH_CHECK();
   return DN_OK;

@@ -10,6 +10,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully-converged warp.  Role loops stay warp-uniform and only the single-thread
+// instructions (tcgen05.mma / commit / TMA issue) are predicated on this, so the compiler keeps
+// descriptors and addresses in uniform registers instead of emitting per-instruction
+// ELECT/BRA.U.ANY "waterfall" loops (measured: ~180 cycles per UTCHMMA issue with `if (lane==0)`).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -52,6 +62,11 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src_gmem), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// contiguous global range -> L2 (no smem destination, no completion tracking)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 
 // ---- tcgen05 ----------------------------------------------------------------------------------
@@ -120,6 +135,14 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   const float r = x - hi;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
   lo = __uint_as_float(l);
+}
+
+// cheaper split for activations: one cvt; lo keeps full fp32 bits (the MMA truncates it to TF32)
+__device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  lo = x - hi;
 }
 
 }  // namespace tc
