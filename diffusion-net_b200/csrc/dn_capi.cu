@@ -246,13 +246,10 @@ int dn_gradient_features_fwd(const dn_csr* grad, const float* x_diffuse, const f
   Bump ws(workspace, ws_bytes);
   const int npq = with_gradient_rotations ? 2 * C : C;
   float* pq = pq_out ? pq_out : ws.take(V * npq);
-  float* wpack = ws.take((int64_t)npq * C);
-  if (!pq || !wpack) return DN_ERR_WORKSPACE;
-  DN_CUDA_TRY(cudaMemcpyAsync(wpack, A_re, sizeof(float) * C * C, cudaMemcpyDeviceToDevice, st));
-  if (with_gradient_rotations)
-    DN_CUDA_TRY(cudaMemcpyAsync(wpack + (int64_t)C * C, A_im, sizeof(float) * C * C, cudaMemcpyDeviceToDevice, st));
+  if (!pq) return DN_ERR_WORKSPACE;
   DnRowsSrc src = one_src(x_diffuse, C, C);
-  DnLayer L = make_layer(wpack, C, 0, nullptr, 0, C, npq, pq, npq);   // [P|Q] = xd [A_re;A_im]^T
+  DnLayer L = make_layer(A_re, C, 0, nullptr, 0, C, npq, pq, npq);   // [P|Q] = xd [A_re;A_im]^T
+  if (with_gradient_rotations) { L.W2 = A_im; L.n_split = C; }
   int rc = run_chain(src, &L, 1, V, engine, nullptr, nullptr, ws.base + ws.off, ws.size - ws.off, st);
   if (rc) return rc;
   return launch_spmm_features(grad, x_diffuse, pq, with_gradient_rotations, V, C, features, st);
@@ -425,41 +422,73 @@ int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const
   float* xd = ws.take(V * C);
   float* pq = p->with_gradient_features ? ws.take(V * npq) : nullptr;
   float* feat = p->with_gradient_features ? ws.take(V * C) : nullptr;
-  float* wpack = p->with_gradient_features ? ws.take((int64_t)npq * C) : nullptr;
   const int64_t pf = kPartialFloats;
   float* partial = ws.take(pf);
-  if (!S || !xd || !partial || (p->with_gradient_features && (!pq || !feat || !wpack))) return DN_ERR_WORKSPACE;
+  if (!S || !xd || !partial || (p->with_gradient_features && (!pq || !feat))) return DN_ERR_WORKSPACE;
   int rc, P = 0;
   // (a1) spectral diffusion: to_basis -> exp(-lambda t) -> from_basis   [layers.py:56-67]
   if ((rc = to_basis_partials(x_in, evecs, mass, V, K, C, partial, pf, &P, engine, st))) return rc;
   if ((rc = launch_spectral_scale(partial, P, evals, p->diffusion_time, K, C, nullptr, S, 1, st))) return rc;
+
+  // every dense layer of the block: [0] from_basis, [1] (a5, commuted) [P|Q] = x_diffuse [A_re;A_im]^T,
+  // [2..] cat -> MiniMLP -> + x_in  [layers.py:229-239]
+  const int nm = p->n_mlp_layers;
+  DnLayer L[2 + DN_MAX_LAYERS];
+  L[0] = make_layer(S, C, 1, nullptr, 0, K, C, xd, C);
+  int nfront = 1;
+  if (p->with_gradient_features) {
+    L[1] = make_layer(p->A_re, C, 0, nullptr, 0, C, npq, pq, npq);
+    if (rot) { L[1].W2 = p->A_im; L[1].n_split = C; }
+    nfront = 2;
+  }
+  const int nsrc = p->with_gradient_features ? 3 : 2;
+  if (p->mlp_dims_host[0] != nsrc * C) return DN_ERR_INVALID_ARGUMENT;
+  int maxn = 0;
+  for (int l = 0; l < nm; ++l) {
+    const bool last = (l + 1 == nm);
+    if (!p->mlp_weight_host[l] || p->mlp_dims_host[l + 1] <= 0) return DN_ERR_INVALID_ARGUMENT;
+    L[nfront + l] = make_layer(p->mlp_weight_host[l], p->mlp_dims_host[l], 0,
+                               p->mlp_bias_host ? p->mlp_bias_host[l] : nullptr, last ? 0 : 1, p->mlp_dims_host[l],
+                               p->mlp_dims_host[l + 1], last ? out : nullptr, p->mlp_dims_host[l + 1]);
+    if (last) { L[nfront + l].residual = x_in; L[nfront + l].ld_res = C; }
+    if (p->mlp_dims_host[l + 1] > maxn) maxn = p->mlp_dims_host[l + 1];
+  }
+  if (p->mlp_dims_host[nm] != C) return DN_ERR_INVALID_ARGUMENT;
+  DnRowsSrc src_fb = one_src(evecs, K, K);
+  DnRowsSrc src_pq = one_src(xd, C, C);
+  DnRowsSrc src_mlp;
+  memset(&src_mlp, 0, sizeof(src_mlp));
+  const float* srcs[3] = {x_in, xd, feat};
+  for (int q = 0; q < nsrc; ++q) { src_mlp.ptr[q] = srcs[q]; src_mlp.width[q] = C; src_mlp.ld[q] = C; }
+  src_mlp.nsrc = nsrc;
+  // one launch packs (hi/lo split + UMMA layout) every weight the tensor-core kernels will stream
+  const bool tc = use_tc(engine) && tc_supported_device();
+  const bool tc_front = tc && tc_rows_chain_supported(src_fb, &L[0], 1) == DN_OK &&
+                        (nfront == 1 || tc_rows_chain_supported(src_pq, &L[1], 1) == DN_OK);
+  const bool tc_mlp = tc && tc_rows_chain_supported(src_mlp, &L[nfront], nm) == DN_OK;
+  if (tc_front || tc_mlp) {
+    DnLayer* first = tc_front ? &L[0] : &L[nfront];
+    const int cnt = (tc_front ? nfront : 0) + (tc_mlp ? nm : 0);
+    const int64_t pb = tc_chain_ws_bytes(first, cnt);
+    float* pk = ws.take(pb / 4);
+    if (!pk) return DN_ERR_WORKSPACE;
+    if ((rc = tc_pack_layers(first, cnt, pk, pb, st))) return rc;
+  }
+  float *t0 = nullptr, *t1 = nullptr;
+  if (!tc_mlp && nm > 1) {
+    t0 = ws.take(V * maxn);
+    t1 = ws.take(V * maxn);
+    if (!t0 || !t1) return DN_ERR_WORKSPACE;
+  }
   void* tcws = ws.base + ws.off;
   const int64_t tcws_bytes = ws.size - ws.off;
-  {
-    DnRowsSrc src = one_src(evecs, K, K);
-    DnLayer L[2];
-    L[0] = make_layer(S, C, 1, nullptr, 0, K, C, xd, C);
-    int nl = 1;
-    if (p->with_gradient_features) {
-      // (a5, commuted) [P|Q] = x_diffuse [A_re;A_im]^T, fused behind from_basis on the same row tile
-      DN_CUDA_TRY(cudaMemcpyAsync(wpack, p->A_re, sizeof(float) * C * C, cudaMemcpyDeviceToDevice, st));
-      if (rot)
-        DN_CUDA_TRY(cudaMemcpyAsync(wpack + (int64_t)C * C, p->A_im, sizeof(float) * C * C,
-                                    cudaMemcpyDeviceToDevice, st));
-      L[1] = make_layer(wpack, C, 0, nullptr, 0, C, npq, pq, npq);
-      nl = 2;
-    }
-    if ((rc = run_chain(src, L, nl, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
-  }
+  if ((rc = run_chain(src_fb, &L[0], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
+  if (nfront == 2)
+    if ((rc = run_chain(src_pq, &L[1], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
   // (a4+a5) sparse tangent gradient + complex inner product + tanh   [layers.py:216-226,128-130]
   if (p->with_gradient_features)
     if ((rc = launch_spmm_features(grad, xd, pq, rot, V, C, feat, st))) return rc;
-  // (a6+a7) cat -> MiniMLP -> + x_in   [layers.py:229-239]
-  const float* srcs[3] = {x_in, xd, feat};
-  const int widths[3] = {C, C, C};
-  return dn_mini_mlp_fwd(srcs, widths, p->with_gradient_features ? 3 : 2, p->mlp_weight_host, p->mlp_bias_host,
-                         p->mlp_dims_host, p->n_mlp_layers, nullptr, x_in, V, nullptr, out, tcws, tcws_bytes, engine,
-                         stream);
+  return run_chain(src_mlp, &L[nfront], nm, V, engine, t0, t1, tcws, tcws_bytes, st);
 }
 
 }  // extern "C"

@@ -30,6 +30,9 @@ struct DnLayer {
   const float* W;        // nn.Linear layout [N][K] (ldw = K) when !w_trans; [K][N] (ldw = N) when w_trans
   int64_t ldw;
   int w_trans;
+  const float* W2;       // optional second block of output rows (!w_trans only): rows n >= n_split
+  int n_split;           //   come from W2[n - n_split]  (stacks [A_re; A_im] without a copy)
+  const float* prepacked;  // optional: weights already in the tensor-core layout (tc_pack_layers)
   const float* bias;     // [N] or null
   int relu;
   const float* emul;     // optional elementwise multiplier [V][N] applied after the activation
@@ -94,3 +97,5 @@ int tc_to_basis_partial(const float* values, const float* basis, const float* ma
                         float* partial, int* P_out, int passes, cudaStream_t st);
 int tc_to_basis_supported(int K, int C);
 int64_t tc_chain_ws_bytes(const DnLayer* layers, int n_layers);
+// one launch: pack the weights of n layers into ws and set layers[i].prepacked
+int tc_pack_layers(DnLayer* layers, int n_layers, void* ws, int64_t ws_bytes, cudaStream_t st);

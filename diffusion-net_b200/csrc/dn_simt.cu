@@ -7,6 +7,7 @@
 //   SpatialGradientFeatures.forward layers.py:117-130, MiniMLP layers.py:133-164.
 #include "dn_internal.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(256) rows_gemm_kernel(DnRowsSrc src, DnLayer L
       const int n = t >> 2, kq = (t & 3) * 4, gn = n0 + n;
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       if (gn < N) {
-        const float* wp = L.W + (int64_t)gn * L.ldw + k0 + kq;
+        const float* wp = (L.W2 && gn >= L.n_split) ? L.W2 + (int64_t)(gn - L.n_split) * L.ldw + k0 + kq
+                                                    : L.W + (int64_t)gn * L.ldw + k0 + kq;
         if (VEC && k0 + kq + 3 < K) {
           float4 q = ldg4(wp);
           v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
@@ -410,6 +412,73 @@ __global__ void __launch_bounds__(256) spmm_features_kernel(const int32_t* __res
 }
 
 // U[v] = [dd*Bre | dd*Bim | dd*gX | dd*gY],  dd = dfeat * (1 - feat^2)
+// Tuned variant for the common case (C/4) % 32 == 0 (one float4 per lane per 128 channels) and rows of <= 32
+// entries: the row's (col, gx, gy) triples are fetched once, coalesced, one per lane, and broadcast with
+// shuffles, so the neighbour-row gathers no longer wait on dependent index loads; NB neighbours are gathered
+// per batch (3*NB independent 16-byte loads in flight per lane).
+template <bool ROT, int NB>
+__global__ void __launch_bounds__(256) spmm_features_v2_kernel(const int32_t* __restrict__ rowptr,
+                                                               const int32_t* __restrict__ colidx,
+                                                               const float2* __restrict__ vals,
+                                                               const float* __restrict__ xd,
+                                                               const float* __restrict__ pq, int ld_pq, int64_t V,
+                                                               int C, float* __restrict__ feat) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= V) return;
+  const int s = __ldg(rowptr + row), ntot = __ldg(rowptr + row + 1) - s;
+  for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
+    float4 gX = make_float4(0.f, 0.f, 0.f, 0.f), gY = gX, bre = gX, bim = gX;
+    for (int base = 0; base < ntot; base += 32) {          // rows longer than a warp: 32 entries at a time
+      const int n = (ntot - base) < 32 ? (ntot - base) : 32;
+      int mycol = 0;
+      float2 myg = make_float2(0.f, 0.f);
+      if (lane < n) {
+        mycol = __ldg(colidx + s + base + lane);
+        myg = __ldg(vals + s + base + lane);
+      }
+      for (int p0 = 0; p0 < n; p0 += NB) {
+        float4 x[NB], P[NB], Q[NB];
+        float gx[NB], gy[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int pj = (p0 + j < n) ? p0 + j : p0;     // clamp: duplicates get weight 0
+          const int64_t col = __shfl_sync(0xffffffffu, mycol, pj);
+          const float wx = __shfl_sync(0xffffffffu, myg.x, pj), wy = __shfl_sync(0xffffffffu, myg.y, pj);
+          gx[j] = (p0 + j < n) ? wx : 0.f;
+          gy[j] = (p0 + j < n) ? wy : 0.f;
+          x[j] = ldg4(xd + col * C + c4 * 4);
+          P[j] = ldg4(pq + col * ld_pq + c4 * 4);
+          if (ROT) Q[j] = ldg4(pq + col * ld_pq + C + c4 * 4);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          gX.x = fmaf(gx[j], x[j].x, gX.x); gX.y = fmaf(gx[j], x[j].y, gX.y);
+          gX.z = fmaf(gx[j], x[j].z, gX.z); gX.w = fmaf(gx[j], x[j].w, gX.w);
+          gY.x = fmaf(gy[j], x[j].x, gY.x); gY.y = fmaf(gy[j], x[j].y, gY.y);
+          gY.z = fmaf(gy[j], x[j].z, gY.z); gY.w = fmaf(gy[j], x[j].w, gY.w);
+          bre.x = fmaf(gx[j], P[j].x, bre.x); bre.y = fmaf(gx[j], P[j].y, bre.y);
+          bre.z = fmaf(gx[j], P[j].z, bre.z); bre.w = fmaf(gx[j], P[j].w, bre.w);
+          bim.x = fmaf(gy[j], P[j].x, bim.x); bim.y = fmaf(gy[j], P[j].y, bim.y);
+          bim.z = fmaf(gy[j], P[j].z, bim.z); bim.w = fmaf(gy[j], P[j].w, bim.w);
+          if (ROT) {
+            bre.x = fmaf(-gy[j], Q[j].x, bre.x); bre.y = fmaf(-gy[j], Q[j].y, bre.y);
+            bre.z = fmaf(-gy[j], Q[j].z, bre.z); bre.w = fmaf(-gy[j], Q[j].w, bre.w);
+            bim.x = fmaf(gx[j], Q[j].x, bim.x); bim.y = fmaf(gx[j], Q[j].y, bim.y);
+            bim.z = fmaf(gx[j], Q[j].z, bim.z); bim.w = fmaf(gx[j], Q[j].w, bim.w);
+          }
+        }
+      }
+    }
+    float4 o;
+    o.x = tanhf(fmaf(gX.x, bre.x, gY.x * bim.x));
+    o.y = tanhf(fmaf(gX.y, bre.y, gY.y * bim.y));
+    o.z = tanhf(fmaf(gX.z, bre.z, gY.z * bim.z));
+    o.w = tanhf(fmaf(gX.w, bre.w, gY.w * bim.w));
+    *reinterpret_cast<float4*>(feat + row * C + c4 * 4) = o;
+  }
+}
+
 template <bool ROT>
 __global__ void __launch_bounds__(256) features_bwd_local_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const float2* __restrict__ vals,
@@ -513,7 +582,8 @@ int simt_rows_gemm(const DnRowsSrc& src, const DnLayer& L, int64_t V, cudaStream
     ktot += src.width[i];
   }
   if (ktot != L.K) return DN_ERR_INVALID_ARGUMENT;
-  vec = vec && (L.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(L.W) & 15) == 0);
+  vec = vec && (L.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(L.W) & 15) == 0) &&
+        (!L.W2 || (reinterpret_cast<uintptr_t>(L.W2) & 15) == 0);
   dim3 grid((unsigned)((V + RG_BM - 1) / RG_BM), (unsigned)((L.N + RG_BN - 1) / RG_BN));
   if (vec)
     rows_gemm_kernel<true><<<grid, 256, 0, st>>>(src, L, V);
@@ -608,10 +678,30 @@ int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int 
                          float* feat, cudaStream_t st) {
   if (V <= 0) return DN_OK;
   if (C % 4) return DN_ERR_UNSUPPORTED;
+  const float2* vals = reinterpret_cast<const float2*>(g->vals);
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("DN_SPMM_VARIANT");
+    // measured on B200 (tools/ablate_spmm.py, V=200k C=128): the kernel is L1/L2-throughput bound, so more
+    // gathers in flight per lane (variants 2,3) are slower; variant 1 wins only on permuted vertex orders
+    variant = e ? atoi(e) : 0;
+  }
+  if ((C % 128) == 0 && variant > 0) {     // one warp per row, one float4 per lane per 128 channels
+    const unsigned blocks = (unsigned)((V * 32 + 255) / 256);
+    const int ld = rotations ? 2 * C : C;
+    if (rotations) {
+      if (variant == 1) spmm_features_v2_kernel<true, 2><<<blocks, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, C, feat);
+      else if (variant == 2) spmm_features_v2_kernel<true, 4><<<blocks, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, C, feat);
+      else spmm_features_v2_kernel<true, 7><<<blocks, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, C, feat);
+    } else {
+      spmm_features_v2_kernel<false, 4><<<blocks, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, C, feat);
+    }
+    DN_LAUNCH_CHECK();
+    return DN_OK;
+  }
   const int G = pick_group(C);
   const int64_t warps = (V + (32 / G) - 1) / (32 / G);
   const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
-  const float2* vals = reinterpret_cast<const float2*>(g->vals);
   if (rotations)
     spmm_features_kernel<true><<<blocks, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, 2 * C, V, C, G, feat);
   else

@@ -59,19 +59,40 @@ struct TcChainParams {
 // ---------------------------------------------------------------------------------------------
 // weight pack:  W -> [chunk][hi | lo][ (k/4)*N*16B + (n/8)*128B + (n%8)*16B + (k%4)*4B ]
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ W, int64_t ldw, int w_trans, int K, int N, int kc,
-                                    float* __restrict__ dst) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= K * N) return;
+struct PackJob {
+  const float* W;
+  const float* W2;
+  float* dst;
+  int64_t ldw;
+  int n_split, w_trans, K, N, blk0;
+};
+struct PackJobs {
+  PackJob j[DN_MAX_LAYERS];
+  int n, kc;
+};
+
+// all weight matrices of a block forward in one launch (blocks are assigned to jobs by blk0)
+__global__ void pack_weights_kernel(const __grid_constant__ PackJobs jobs) {
+  int ji = 0;
+#pragma unroll
+  for (int i = 1; i < DN_MAX_LAYERS; ++i)
+    if (i < jobs.n && (int)blockIdx.x >= jobs.j[i].blk0) ji = i;
+  const PackJob& J = jobs.j[ji];
+  const int idx = ((int)blockIdx.x - J.blk0) * blockDim.x + threadIdx.x;
+  if (idx >= J.K * J.N) return;
+  const int K = J.K, N = J.N, kc = jobs.kc;
   const int n = idx / K, k = idx % K;
-  const float w = w_trans ? W[(int64_t)k * ldw + n] : W[(int64_t)n * ldw + k];
+  float w;
+  if (J.w_trans) w = J.W[(int64_t)k * J.ldw + n];
+  else if (J.W2 && n >= J.n_split) w = J.W2[(int64_t)(n - J.n_split) * J.ldw + k];
+  else w = J.W[(int64_t)n * J.ldw + k];
   float hi, lo;
   split_tf32(w, hi, lo);
   const int chunk = k / kc, kk = k % kc;
   const int64_t img = (int64_t)N * kc;   // floats per image
   const int64_t off = (int64_t)chunk * 2 * img + (int64_t)(kk >> 2) * (N * 4) + (n >> 3) * 32 + (n & 7) * 4 + (kk & 3);
-  dst[off] = hi;
-  dst[off + img] = lo;
+  J.dst[off] = hi;
+  J.dst[off + img] = lo;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -598,6 +619,7 @@ int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_l
     const DnLayer& L = layers[l];
     if (L.K % 16 || L.K < 16 || L.N % 16 || L.N < 16 || L.N > 256) return DN_ERR_UNSUPPORTED;
     if (L.emul || L.relu_mask_src) return DN_ERR_UNSUPPORTED;
+    if (L.W2 && L.w_trans) return DN_ERR_UNSUPPORTED;
     if (L.bias && (reinterpret_cast<uintptr_t>(L.bias) & 15)) return DN_ERR_UNSUPPORTED;
     if (L.residual && (L.res_scale != 1.f || L.ld_res % 4 || (reinterpret_cast<uintptr_t>(L.residual) & 15)))
       return DN_ERR_UNSUPPORTED;
@@ -616,11 +638,44 @@ int64_t tc_chain_ws_bytes(const DnLayer* layers, int n_layers) {
   return b;
 }
 
-int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers, int n_layers, int64_t V, int passes, void* ws,
+int tc_pack_layers(DnLayer* layers, int n_layers, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (n_layers < 1 || n_layers > DN_MAX_LAYERS) return DN_ERR_INVALID_ARGUMENT;
+  if (tc_chain_ws_bytes(layers, n_layers) > ws_bytes || !ws) return DN_ERR_WORKSPACE;
+  PackJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  jobs.n = n_layers;
+  jobs.kc = KC;
+  char* wp = static_cast<char*>(ws);
+  int blocks = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    DnLayer& L = layers[l];
+    PackJob& J = jobs.j[l];
+    J.W = L.W; J.W2 = L.W2; J.n_split = L.n_split; J.ldw = L.ldw; J.w_trans = L.w_trans; J.K = L.K; J.N = L.N;
+    J.dst = reinterpret_cast<float*>(wp);
+    J.blk0 = blocks;
+    blocks += (L.K * L.N + 255) / 256;
+    L.prepacked = J.dst;
+    wp += ((int64_t)L.K * L.N * 2 * 4 + 255) / 256 * 256;
+  }
+  pack_weights_kernel<<<blocks, 256, 0, st>>>(jobs);
+  DN_LAUNCH_CHECK();
+  return DN_OK;
+}
+
+int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers_in, int n_layers, int64_t V, int passes, void* ws,
                   int64_t ws_bytes, cudaStream_t st) {
   if (V <= 0) return DN_OK;
   if (!tc_supported_device()) return DN_ERR_NOT_SM100;
-  if (tc_chain_ws_bytes(layers, n_layers) > ws_bytes || !ws) return DN_ERR_WORKSPACE;
+  DnLayer layers[DN_MAX_LAYERS];
+  bool packed = true;
+  for (int l = 0; l < n_layers; ++l) {
+    layers[l] = layers_in[l];
+    packed = packed && layers[l].prepacked != nullptr;
+  }
+  if (!packed) {
+    int rc = tc_pack_layers(layers, n_layers, ws, ws_bytes, st);
+    if (rc) return rc;
+  }
   TcChainParams p;
   memset(&p, 0, sizeof(p));
   p.src = src;
@@ -630,21 +685,16 @@ int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers, int n_layers, int
   p.V = V;
   p.nmax = 128;
   p.prefetch = 1;
+  p.kch = KC;
   for (int l = 0; l < n_layers; ++l)
     if (layers[l].N > 128) p.nmax = 256;
-  p.kch = KC;
   for (int s = 0; s < src.nsrc; ++s)
     if (src.ld[s] != src.width[s]) p.prefetch = 0;
-  char* wp = static_cast<char*>(ws);
   for (int l = 0; l < n_layers; ++l) {
     const DnLayer& L = layers[l];
-    float* dst = reinterpret_cast<float*>(wp);
-    pack_weights_kernel<<<(L.K * L.N + 255) / 256, 256, 0, st>>>(L.W, L.ldw, L.w_trans, L.K, L.N, p.kch, dst);
-    DN_LAUNCH_CHECK();
     TcLayer& T = p.layer[l];
-    T.wpack = dst; T.bias = L.bias; T.residual = L.residual; T.ld_res = L.ld_res; T.row_scale = L.row_scale;
+    T.wpack = L.prepacked; T.bias = L.bias; T.residual = L.residual; T.ld_res = L.ld_res; T.row_scale = L.row_scale;
     T.out = L.out; T.ld_out = L.ld_out; T.K = L.K; T.N = L.N; T.relu = L.relu;
-    wp += ((int64_t)L.K * L.N * 2 * 4 + 255) / 256 * 256;
   }
   const int64_t ntiles = (V + TILE_M - 1) / TILE_M;
   const int grid = (int)(ntiles < 2 * g_sm_count ? ntiles : 2 * g_sm_count);
