@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default=os.environ.get("DN_B200_ENGINE", "tc3x"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -259,19 +259,27 @@ def main():
     pipe.result(pipe.submit(h, out_hosts[0]))          # warm-up (allocator, CSR prep path)
     barrier()
     main = torch.cuda.current_stream(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(main)
-    last = None
-    for i in range(args.e2e_steps):
-        last = pipe.submit(h, out_hosts[i & 1])
-    main.wait_event(last["fin"])                       # the last result has landed in host memory
-    e1.record(main)
-    pipe.drain()
-    barrier()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_val = world * V / (float(e2e_ms.item()) / args.e2e_steps * 1e-3) / 1e6
+    def timed_pipe(pp, hin):
+        """median over 3 repeats of `e2e_steps` pipelined steps (host-link throughput on shared boxes is noisy)"""
+        reps = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(main)
+            lastt = None
+            for i in range(args.e2e_steps):
+                lastt = pp.submit(hin, out_hosts[i & 1])
+            main.wait_event(lastt["fin"])                  # the last result has landed in host memory
+            b.record(main)
+            pp.drain()
+            barrier()
+            reps.append(a.elapsed_time(b))
+        reps.sort()
+        t = torch.tensor([reps[1]], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / args.e2e_steps
+
+    e2e_val = world * V / (timed_pipe(pipe, h) * 1e-3) / 1e6
 
     # same pipeline with the operator tuple kept resident on the device (SURVEY.md 8f row 2): only the
     # features go up and the result comes down each step -- reported beside e2e, not as e2e
@@ -281,18 +289,7 @@ def main():
     pipe2 = dn.streaming.StreamedForward(res_fn, dev, depth=2)
     pipe2.result(pipe2.submit({"x": h["x"]}, out_hosts[0]))
     barrier()
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r0.record(main)
-    for i in range(args.e2e_steps):
-        last = pipe2.submit({"x": h["x"]}, out_hosts[i & 1])
-    main.wait_event(last["fin"])
-    r1.record(main)
-    pipe2.drain()
-    barrier()
-    res_ms = torch.tensor([r0.elapsed_time(r1)], device=dev)
-    if world > 1:
-        dist.all_reduce(res_ms, op=dist.ReduceOp.MAX)
-    e2e_resident = world * V / (float(res_ms.item()) / args.e2e_steps * 1e-3) / 1e6
+    e2e_resident = world * V / (timed_pipe(pipe2, {"x": h["x"]}) * 1e-3) / 1e6
 
     # ---- per-stage device times (rank 0): which kernel dominates, and its roofline ----
     roof, stages = None, None

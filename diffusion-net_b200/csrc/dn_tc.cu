@@ -126,21 +126,21 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
   uint8_t* smA = smem;
   uint8_t* smB = smem + NSA * A_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSA * A_STAGE + B_BYTES);
-  // bars: a_full[NSA] a_empty[NSA] b_full[4] b_empty[4] d_full[2] d_empty[2]
-  const uint32_t a_full = smem_u32(bars), a_empty = smem_u32(bars + NSA);
-  const uint32_t b_full = smem_u32(bars + 2 * NSA), b_empty = smem_u32(bars + 2 * NSA + 4);
-  const uint32_t d_full = smem_u32(bars + 2 * NSA + 8), d_empty = smem_u32(bars + 2 * NSA + 10);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSA + 12);
+  // bars: full[NSA] empty[NSA] d_full[2] d_empty[2].  One full/empty pair per pipeline stage covers both the
+  // activation chunk (4 worker-warp arrivals) and the weight chunk (1 arrive.expect_tx + TMA bytes): the MMA
+  // warp waits once and commits once per K-chunk.
+  const uint32_t full = smem_u32(bars), empty = smem_u32(bars + NSA);
+  const uint32_t d_full = smem_u32(bars + 2 * NSA), d_empty = smem_u32(bars + 2 * NSA + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSA + 4);
 
   const int nmax = p.nmax;                                  // 128 or 256: widest layer
   const uint32_t b_stage = 2u * (uint32_t)nmax * KC * 4;    // hi + lo weight chunk (16 or 32 KiB)
-  const uint32_t nsb = B_BYTES / b_stage;                   // 4 or 2 weight stages
+  const uint32_t NS = (nmax == 128) ? (uint32_t)NSA : 2u;   // pipeline depth (A and B rings alike)
   const uint32_t nbuf = 256u / (uint32_t)nmax;              // 2 or 1 accumulator buffers in TMEM
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSA; ++i) { mbar_init(a_full + 8 * i, 4); mbar_init(a_empty + 8 * i, 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+    for (int i = 0; i < NSA; ++i) { mbar_init(full + 8 * i, 5); mbar_init(empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(d_full + 8 * i, 1); mbar_init(d_empty + 8 * i, 8); }
     fence_barrier_init();
   }
@@ -172,17 +172,17 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
         const uint32_t bytes = p.passes == 3 ? 2 * img_bytes : img_bytes;
         const float* wsrc = p.layer[l].wpack;
         for (int c = 0; c < nch; ++c) {
-          mbar_wait(b_empty + 8 * s, ph ^ 1);
+          mbar_wait(empty + 8 * s, ph ^ 1);
           if (elect_one()) {
             if (p.variant & 32) {      // timing ablation only
-              mbar_arrive(b_full + 8 * s);
+              mbar_arrive(full + 8 * s);
             } else {
-              mbar_arrive_expect_tx(b_full + 8 * s, bytes);
-              tma_bulk_g2s(smem_u32(smB + s * b_stage), wsrc + (int64_t)c * 2 * N * KC, bytes, b_full + 8 * s);
+              mbar_arrive_expect_tx(full + 8 * s, bytes);
+              tma_bulk_g2s(smem_u32(smB + s * b_stage), wsrc + (int64_t)c * 2 * N * KC, bytes, full + 8 * s);
             }
           }
           __syncwarp();
-          if (++s == nsb) { s = 0; ph ^= 1; }
+          if (++s == NS) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
     // constant increments of the address field
     const uint64_t tmplA = (p.variant & 1) ? make_desc(0, 128, A_LBO) : make_desc(0, A_LBO, 128);
     const uint32_t smA_u = smem_u32(smA) >> 4, smB_u = smem_u32(smB) >> 4;
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, g = 0;
+    uint32_t sa = 0, pa = 0, g = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
       for (int l = 0; l < L; ++l, ++g) {
         const int N = p.layer[l].N, nch = p.layer[l].K / KC;
@@ -207,12 +207,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
           tc_fence_after();
         }
         for (int c = 0; c < nch; ++c) {
-          mbar_wait(a_full + 8 * sa, pa);
-          mbar_wait(b_full + 8 * sb, pb);
+          mbar_wait(full + 8 * sa, pa);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t dah = tmplA + (smA_u + sa * (A_STAGE >> 4));
-            const uint64_t dbh = tmplB + (smB_u + sb * (b_stage >> 4));
+            const uint64_t dbh = tmplB + (smB_u + sa * (b_stage >> 4));
 #pragma unroll
             for (int ks = 0; ks < KC / 8; ++ks) {
               const uint64_t a_h = dah + ks * ((2 * A_LBO) >> 4), b_h = dbh + ks * b_ks_u;
@@ -225,13 +224,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
                 mma_tf32_ss(d_tmem, a_h, b_h, idesc, acc);
               }
             }
-            mma_commit(a_empty + 8 * sa);
-            mma_commit(b_empty + 8 * sb);
+            mma_commit(empty + 8 * sa);
             if (c + 1 == nch) mma_commit(d_full + 8 * buf);
           }
           __syncwarp();
-          if (++sa == NSA) { sa = 0; pa ^= 1; }
-          if (++sb == nsb) { sb = 0; pb ^= 1; }
+          if (++sa == NS) { sa = 0; pa ^= 1; }
         }
       }
   } else {
@@ -255,15 +252,15 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
                                : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto store_chunk = [&](uint32_t cidx, const float4* r) {
-      const uint32_t s = cidx % NSA, ph = (cidx / NSA) & 1;
-      mbar_wait(a_empty + 8 * s, ph ^ 1);
+      const uint32_t s = cidx % NS, ph = (cidx / NS) & 1;
+      mbar_wait(empty + 8 * s, ph ^ 1);
       uint8_t* a_hi = smA + s * A_STAGE + cv_off;
 #pragma unroll
       for (int it = 0; it < 4; ++it)
         if (!(p.variant & 64)) store_split4(a_hi, a_hi + A_IMG, it * 128, r[it], p.passes);
       if (!(p.variant & 2)) fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full + 8 * s);
+      if (lane == 0) mbar_arrive(full + 8 * s);
     };
     float4 r[4];
     if ((int64_t)blockIdx.x < ntiles && wg < nch0) load_chunk((int64_t)blockIdx.x * TILE_M, wg, r);
@@ -337,8 +334,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
             for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           if (has_next) {
-            const uint32_t cidx = ci_next + c, s = cidx % NSA, ph = (cidx / NSA) & 1;
-            mbar_wait(a_empty + 8 * s, ph ^ 1);
+            const uint32_t cidx = ci_next + c, s = cidx % NS, ph = (cidx / NS) & 1;
+            mbar_wait(empty + 8 * s, ph ^ 1);
             uint8_t* a_hi = smA + s * A_STAGE + ep_off;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -347,7 +344,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
                              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), p.passes);
             if (!(p.variant & 2)) fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_full + 8 * s);
+            if (lane == 0) mbar_arrive(full + 8 * s);
           }
         }
         // accumulator buffer drained: hand it back to the MMA warp
