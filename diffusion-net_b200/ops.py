@@ -48,13 +48,20 @@ def _stream():
 
 
 _workspaces = {}
+_retired_workspaces = []
+pin_workspaces = False      # set by graphs.GraphedNet: never free a workspace a graph may point into
 
 
 def workspace(V, K, C_, device):
+    """Scratch for the C-ABI calls, one buffer per (device, stream): calls on different streams
+    (graphs.GraphedNet replays meshes concurrently) never share scratch."""
     need = _lib.load().dn_workspace_bytes(int(V), int(K), int(C_))
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev_index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
+        if ws is not None and pin_workspaces:
+            _retired_workspaces.append(ws)     # captured CUDA graphs hold raw pointers into it
         ws = torch.empty(need, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws

@@ -288,3 +288,38 @@ def test_full_size_properties(dn, engine):
         assert O.rel_err(p2.cpu().numpy(), p1.cpu().numpy()) < 2e-5
     gold = _oracle_block(ops_t, params, x)
     assert O.rel_err(out[0].cpu().numpy(), gold) < TOL[engine]
+
+
+def test_graphed_net_and_streamed_forward(dn):
+    """CUDA-graph replay (launch-bound small meshes) and the host-streaming helper reproduce the eager forward."""
+    dn.set_engine("tc3x")
+    C, K = 32, 32
+    net = dn.DiffusionNet(C_in=3, C_out=5, C_width=C, N_block=2, dropout=False).cuda().eval()
+    with torch.no_grad():
+        for n_, p_ in net.named_parameters():
+            if n_.endswith("diffusion_time"):
+                p_.uniform_(1e-3, 0.3)
+    items, refs = [], []
+    for i in range(5):
+        mass, L, evals, evecs, gX, gY = dn.synthetic.structural_operators(12 + i, 16, K, seed=i, device="cuda")
+        x = torch.randn((12 + i) * 16, 3, generator=torch.Generator().manual_seed(i)).cuda()
+        items.append(dict(x_in=x, mass=mass, evals=evals, evecs=evecs, gradX=gX, gradY=gY))
+        with torch.no_grad():
+            refs.append(net(**items[-1]).clone())
+    gn = dn.graphs.GraphedNet(net, n_streams=2)
+    for _ in range(2):                                   # capture, then pure replay
+        outs = gn.forward_batch(items)
+        torch.cuda.synchronize()
+        for o, r in zip(outs, refs):
+            assert torch.equal(o, r)
+    # host pipeline: same result as the eager call on device tensors
+    host = {k: v.cpu().pin_memory() for k, v in items[0].items() if not v.is_sparse}
+    gX, gY = items[0]["gradX"], items[0]["gradY"]
+    def fn(x_in, mass, evals, evecs):
+        with torch.no_grad():
+            return net(x_in, mass, evals=evals, evecs=evecs, gradX=gX, gradY=gY)
+    pipe = dn.streaming.StreamedForward(fn, torch.device("cuda", 0), depth=2)
+    tickets = [pipe.submit(host) for _ in range(3)]
+    for t in tickets:
+        assert torch.equal(pipe.result(t), refs[0].cpu())
+    assert pipe.h2d_bytes == 3 * sum(v.numel() * v.element_size() for v in host.values())
