@@ -158,8 +158,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
     uint32_t s = 0, ph = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t nt = tile + gridDim.x;
-      if (p.prefetch && nt < ntiles && elect_one()) {
-        // the next tile's 128 rows of every source are one contiguous block: pull them into L2 now
+      if (p.prefetch && (p.variant & 512) && nt < ntiles && elect_one()) {   // off by default: see below
+        // the next tile's 128 rows of every source are one contiguous block: pull them into L2 now.
+        // Measured (tools/ablate_mlp.py): this doubled the kernel's DRAM reads (564 vs 308 MB, ncu) and cost
+        // 10 % of its time, so it is disabled unless DN_TC_VARIANT has bit 512 set.
         const int64_t r0 = nt * TILE_M;
         const int64_t rows = (p.V - r0) < TILE_M ? (p.V - r0) : TILE_M;
         for (int q = 0; q < p.src.nsrc; ++q)

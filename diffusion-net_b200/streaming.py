@@ -11,6 +11,16 @@ from __future__ import annotations
 import torch
 
 
+class _Ticket:
+    __slots__ = ("out", "fin", "dev")
+
+    def __init__(self, out, fin, dev):
+        self.out, self.fin, self.dev = out, fin, dev
+
+    def __getitem__(self, k):          # dict-style access kept for callers
+        return getattr(self, k)
+
+
 class StreamedForward:
     """``fn(**device_inputs) -> device tensor`` driven from pinned host buffers.
 
@@ -55,20 +65,19 @@ class StreamedForward:
             fin = torch.cuda.Event()
             fin.record(self.s_out)
         self.d2h_bytes += out_host.numel() * out_host.element_size()
-        ticket = {"out": out_host, "fin": fin, "dev": dev}
+        ticket = _Ticket(out_host, fin, dev)
         self.inflight.append(ticket)
         return ticket
 
     @staticmethod
     def _retire(ticket):
-        ticket["fin"].synchronize()
-        ticket["dev"] = None
+        ticket.fin.synchronize()
+        ticket.dev = None
 
     def result(self, ticket):
         self._retire(ticket)
-        if ticket in self.inflight:
-            self.inflight.remove(ticket)
-        return ticket["out"]
+        self.inflight = [t for t in self.inflight if t is not ticket]
+        return ticket.out
 
     def drain(self):
         while self.inflight:

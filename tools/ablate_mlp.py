@@ -18,7 +18,7 @@ def t_ms(fn, n=10):
     for _ in range(n): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
-names = {0: "baseline", 30: "no fence/loads/mma/tmemld", 62: "  + no weight TMA", 94: "  + no STS (w/ weight TMA)",
+names = {0: "baseline", 512: "only: WITH L2 bulk prefetch", 30: "no fence/loads/mma/tmemld", 62: "  + no weight TMA", 94: "  + no STS (w/ weight TMA)",
          158: "  + no global stores", 286: "  + no bias/residual loads", 510: "all off", 32: "only: no weight TMA",
          64: "only: no STS", 128: "only: no global stores", 256: "only: no bias/residual"}
 with torch.no_grad():
