@@ -256,7 +256,8 @@ def main():
     # download(i-1) on three streams
     pipe = dn.streaming.StreamedForward(e2e_fn, dev, depth=2)
     out_hosts = [out_host, torch.empty(V, C_WIDTH).pin_memory()]
-    pipe.result(pipe.submit(h, out_hosts[0]))          # warm-up (allocator, CSR prep path)
+    for _ in range(3):                                  # warm-up: allocator, CSR prep path, host link
+        pipe.result(pipe.submit(h, out_hosts[0]))
     barrier()
     main = torch.cuda.current_stream(dev)
     def timed_pipe(pp, hin):
@@ -287,7 +288,8 @@ def main():
         with torch.no_grad():
             return blk(x.unsqueeze(0), mb, None, eb, vb, [gradX], [gradY])[0]
     pipe2 = dn.streaming.StreamedForward(res_fn, dev, depth=2)
-    pipe2.result(pipe2.submit({"x": h["x"]}, out_hosts[0]))
+    for _ in range(2):
+        pipe2.result(pipe2.submit({"x": h["x"]}, out_hosts[0]))
     barrier()
     e2e_resident = world * V / (timed_pipe(pipe2, {"x": h["x"]}) * 1e-3) / 1e6
 
@@ -339,6 +341,13 @@ def main():
         else:
             roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": gbs / pk["hbm_gbs"], "traffic": None}
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` launch (profiles/)
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+                tj = json.load(fh)["rows_chain_kernel#1"]
+            roof["traffic"] = (tj["dram_read_mb"] + tj["dram_write_mb"]) * 1e6
+            roof["traffic_unit"] = "bytes per launch (algorithmic: {:.0f})".format(mlp_bytes)
+        except Exception:
+            pass
         roof.update({"kernel": "rows_chain_kernel (MiniMLP+skip)", "ms": st_mlp, "peak_source": pk["source"],
                      "issued_flop_factor": passes,
                      "note": "achieved = algorithmic fp32 flops / CUDA-event time, peak = measured bf16 cuBLAS burst; "

@@ -54,6 +54,7 @@ struct TcChainParams {
   int kch;        // K-chunk size the kernel instance uses (16 or 32)
   int prefetch;   // sources are row-contiguous: bulk-prefetch the next tile into L2
   int64_t V;
+  long long* trace;   // optional (tools/trace_chain.py): per-warp (event, clock64) pairs of CTA 0
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -109,6 +110,16 @@ __device__ __forceinline__ void store_split4(uint8_t* a_hi, uint8_t* a_lo, uint3
   if (passes == 3) *reinterpret_cast<float4*>(a_lo + byte_off) = l;
 }
 
+#define DN_TRACE_MAX 4096
+#define DN_TRACE(ev)                                                                  \
+  do {                                                                                \
+    if (p.trace && blockIdx.x == 0 && lane == 0 && tr_n < DN_TRACE_MAX) {             \
+      p.trace[((int64_t)warp * DN_TRACE_MAX + tr_n) * 2] = (ev);                      \
+      p.trace[((int64_t)warp * DN_TRACE_MAX + tr_n) * 2 + 1] = clock64();             \
+      ++tr_n;                                                                         \
+    }                                                                                 \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // fused affine chain over 128-row tiles
 //
@@ -139,12 +150,22 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
   const uint32_t nbuf = 256u / (uint32_t)nmax;              // 2 or 1 accumulator buffers in TMEM
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tr_n = 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSA; ++i) { mbar_init(full + 8 * i, 5); mbar_init(empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(d_full + 8 * i, 1); mbar_init(d_empty + 8 * i, 8); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<256>(smem_u32(tmem_slot));
+  // biases of every layer are staged once in the unused tail of the weight ring (N<=128 chains use 48 of
+  // its 64 KiB): the epilogues read them with broadcast LDS instead of per-chunk global loads
+  float* sbias = reinterpret_cast<float*>(smB + 3 * 16384);
+  const bool bias_in_smem = (nmax == 128);
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < p.n_layers * 128; i += blockDim.x) {
+      const int l = i >> 7, n = i & 127;
+      sbias[i] = (p.layer[l].bias && n < p.layer[l].N) ? __ldg(p.layer[l].bias + n) : 0.f;
+    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -174,7 +195,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
         const uint32_t bytes = p.passes == 3 ? 2 * img_bytes : img_bytes;
         const float* wsrc = p.layer[l].wpack;
         for (int c = 0; c < nch; ++c) {
+          DN_TRACE(30);
           mbar_wait(empty + 8 * s, ph ^ 1);
+          DN_TRACE(31);
           if (elect_one()) {
             if (p.variant & 32) {      // timing ablation only
               mbar_arrive(full + 8 * s);
@@ -209,7 +232,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
           tc_fence_after();
         }
         for (int c = 0; c < nch; ++c) {
+          DN_TRACE(20);
           mbar_wait(full + 8 * sa, pa);
+          DN_TRACE(21);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t dah = tmplA + (smA_u + sa * (A_STAGE >> 4));
@@ -230,6 +255,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
             if (c + 1 == nch) mma_commit(d_full + 8 * buf);
           }
           __syncwarp();
+          DN_TRACE(22);
           if (++sa == NS) { sa = 0; pa ^= 1; }
         }
       }
@@ -242,30 +268,47 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
     const int nch0 = p.layer[0].K / KC;
     // byte offset of this lane's 16-byte slot inside an operand image, conversion mapping
     const uint32_t cv_off = kg * A_LBO + (4 * quarter) * 128 + rl * 16;     // + it * 128
-    auto load_chunk = [&](int64_t row0_, int c, float4* r) {
+    // per-tile row pointers of this lane (one per source); a chunk load is then pointer + column offset
+    const float* rowp[DN_MAX_SRC];
+    int64_t rem_rows = 0;
+    auto set_tile = [&](int64_t row0_) {
+      const int64_t rfirst = row0_ + 32 * quarter + rl;
+      rem_rows = p.V - rfirst;
+#pragma unroll
+      for (int q = 0; q < DN_MAX_SRC; ++q)
+        rowp[q] = (q < p.src.nsrc) ? p.src.ptr[q] + rfirst * p.src.ld[q] + 4 * kg : nullptr;
+    };
+    auto load_chunk = [&](int c, float4* r) {
       int k0 = c * KC, s = 0;
       while (s + 1 < p.src.nsrc && k0 >= p.src.width[s]) { k0 -= p.src.width[s]; ++s; }
-      const int64_t ld = p.src.ld[s];
-      const float* base = p.src.ptr[s] + k0 + 4 * kg + (row0_ + 32 * quarter + rl) * ld;
-      const int64_t rem = p.V - (row0_ + 32 * quarter + rl);
+      const float* base = (s == 0 ? rowp[0] : (s == 1 ? rowp[1] : rowp[2])) + k0;
+      const int64_t st8 = 8 * p.src.ld[s];
 #pragma unroll
       for (int it = 0; it < 4; ++it)
-        r[it] = (8 * it < rem && !(p.variant & 4)) ? __ldg(reinterpret_cast<const float4*>(base + 8 * it * ld))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        r[it] = (8 * it < rem_rows && !(p.variant & 4)) ? __ldg(reinterpret_cast<const float4*>(base + it * st8))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto store_chunk = [&](uint32_t cidx, const float4* r) {
       const uint32_t s = cidx % NS, ph = (cidx / NS) & 1;
+      DN_TRACE(1);
       mbar_wait(empty + 8 * s, ph ^ 1);
+      DN_TRACE(2);
       uint8_t* a_hi = smA + s * A_STAGE + cv_off;
 #pragma unroll
       for (int it = 0; it < 4; ++it)
         if (!(p.variant & 64)) store_split4(a_hi, a_hi + A_IMG, it * 128, r[it], p.passes);
+      DN_TRACE(3);
       if (!(p.variant & 2)) fence_proxy_async();
       __syncwarp();
+      DN_TRACE(4);
       if (lane == 0) mbar_arrive(full + 8 * s);
+      DN_TRACE(5);
     };
     float4 r[4];
-    if ((int64_t)blockIdx.x < ntiles && wg < nch0) load_chunk((int64_t)blockIdx.x * TILE_M, wg, r);
+    if ((int64_t)blockIdx.x < ntiles) {
+      set_tile((int64_t)blockIdx.x * TILE_M);
+      if (wg < nch0) load_chunk(wg, r);
+    }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t row0 = tile * TILE_M;
       for (int l = 0; l < L; ++l, ++g) {
@@ -274,10 +317,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
         if (l == 0) {
           for (int c = wg; c < nch; c += 2) {
             store_chunk(ci + c, r);
-            if (c + 2 < nch) load_chunk(row0, c + 2, r);
+            if (c + 2 < nch) load_chunk(c + 2, r);
           }
           const int64_t nt = tile + gridDim.x;   // first chunk of the next tile: hidden behind the epilogues
-          if (nt < ntiles && wg < nch0) load_chunk(nt * TILE_M, wg, r);
+          if (nt < ntiles) {
+            set_tile(nt * TILE_M);
+            if (wg < nch0) load_chunk(wg, r);
+          }
         }
         const uint32_t ci_next = ci + nch;
         // ---- epilogue of layer l (and operand production for layer l+1)
@@ -296,7 +342,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
         float4 res[4];
         if (has_res && wg < nco) load_res(wg, res);     // requested before waiting for the accumulator
         const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
+        DN_TRACE(10);
         mbar_wait(d_full + 8 * buf, use & 1);
+        DN_TRACE(11);
         tc_fence_after();
         const uint32_t d_lane = tmem_base + ((uint32_t)(32 * quarter) << 16) + buf * (uint32_t)nmax;
         for (int c = wg; c < nco; c += 2) {
@@ -306,12 +354,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 1.f;
           }
+          DN_TRACE(12);
           const int n0 = c * KC;
           if (Lr.bias && !(p.variant & 256)) {
-            const float4* bp = reinterpret_cast<const float4*>(Lr.bias + n0);
+            const float4* bp = bias_in_smem ? reinterpret_cast<const float4*>(sbias + l * 128 + n0)
+                                            : reinterpret_cast<const float4*>(Lr.bias + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 b = __ldg(bp + j);
+              const float4 b = bp[j];
               v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
           }
@@ -330,14 +380,17 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
             }
             if (c + 2 < nco) load_res(c + 2, res);
           }
+          DN_TRACE(13);
           if (Lr.out && row < p.V && !(p.variant & 128)) {
             float4* op = reinterpret_cast<float4*>(Lr.out + row * Lr.ld_out + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
+          DN_TRACE(14);
           if (has_next) {
             const uint32_t cidx = ci_next + c, s = cidx % NS, ph = (cidx / NS) & 1;
             mbar_wait(empty + 8 * s, ph ^ 1);
+            DN_TRACE(15);
             uint8_t* a_hi = smA + s * A_STAGE + ep_off;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -347,6 +400,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
             if (!(p.variant & 2)) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(full + 8 * s);
+            DN_TRACE(16);
           }
         }
         // accumulator buffer drained: hand it back to the MMA warp
@@ -570,6 +624,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
 }
 
 int g_tc_ok = -1;
+long long* g_trace_ptr = nullptr;
 int g_sm_count = 0;
 
 int env_variant() {
@@ -578,6 +633,8 @@ int env_variant() {
 }
 
 }  // namespace
+
+extern "C" void dn_debug_set_trace(void* device_buffer) { g_trace_ptr = static_cast<long long*>(device_buffer); }
 
 bool tc_supported_device() {
   if (g_tc_ok < 0) {
@@ -682,6 +739,7 @@ int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers_in, int n_layers, 
   p.passes = passes;
   p.variant = env_variant();
   p.V = V;
+  p.trace = g_trace_ptr;
   p.nmax = 128;
   p.prefetch = 1;
   p.kch = KC;

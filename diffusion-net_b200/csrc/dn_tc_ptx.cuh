@@ -137,11 +137,11 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = __uint_as_float(l);
 }
 
-// cheaper split for activations: one cvt; lo keeps full fp32 bits (the MMA truncates it to TF32)
+// cheaper split for activations: hi = x rounded to TF32 (round-half-up on the magnitude bits: IADD + LOP
+// instead of the 4-instruction cvt.rna emulation); lo = x - hi is exact in fp32 and the MMA reads only its
+// top 19 bits.  Non-finite inputs stay non-finite.
 __device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   lo = x - hi;
 }
 
