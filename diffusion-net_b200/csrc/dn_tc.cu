@@ -418,6 +418,254 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
 }
 
 // ---------------------------------------------------------------------------------------------
+// fused affine chain, activations in TMEM (tcgen05.mma with the A operand read from tensor memory)
+//
+// The smem-operand kernel above moves ~80 KB through shared memory per 16-wide K-chunk (MMA reads of the
+// hi/lo activation and weight images, the operand stores, the weight TMA writes) and its trace shows every
+// MIO operation (STS, fence.proxy.async, mbarrier, LDG/STG issue) queueing behind that traffic.  Here the
+// activation chunks live in TMEM: workers write x = hi + lo with tcgen05.st (one lane per row, the same
+// lane<->row mapping tcgen05.ld gives the epilogue, so no transposes and no bank conflicts), the MMA reads A
+// from TMEM and only the weight chunks stay in shared memory (40 KB per chunk).  TMEM: columns [0,256)
+// accumulators (2 x 128 ping-pong, or 1 x 256), [256,512) an 8-stage ring of (hi16 | lo16) column blocks.
+// One CTA per SM: warp 0 weight TMA, warp 1 MMA, warps 2..17 = four worker warpgroups (K-chunk c -> c % 4).
+// ---------------------------------------------------------------------------------------------
+constexpr int TS_THREADS = 576;
+constexpr int TS_NSA = 8;                    // activation stages in TMEM
+constexpr int TS_ACOL = 256;                 // first TMEM column of the activation ring
+constexpr int TS_BIAS_FLOATS = DN_MAX_LAYERS * 256;
+constexpr int TS_BBYTES = 131072;            // weight ring: 8 stages at N<=128, 4 at N=256
+constexpr int TS_SMEM = TS_BBYTES + TS_BIAS_FLOATS * 4 + 512;
+
+__global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __grid_constant__ TcChainParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smB = smem;
+  float* sbias = reinterpret_cast<float*>(smem + TS_BBYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS_BBYTES + TS_BIAS_FLOATS * 4);
+  // bars: a_full[8] a_empty[8] b_full[8] b_empty[8] d_full[2] d_empty[2]
+  const uint32_t a_full = smem_u32(bars), a_empty = smem_u32(bars + TS_NSA);
+  const uint32_t b_full = smem_u32(bars + 2 * TS_NSA), b_empty = smem_u32(bars + 2 * TS_NSA + 8);
+  const uint32_t d_full = smem_u32(bars + 2 * TS_NSA + 16), d_empty = smem_u32(bars + 2 * TS_NSA + 18);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TS_NSA + 20);
+
+  const int nmax = p.nmax;
+  const uint32_t b_stage = 2u * (uint32_t)nmax * KC * 4;    // hi + lo weight chunk (16 or 32 KiB)
+  const uint32_t nsb = TS_BBYTES / b_stage;                 // 8 or 4
+  const uint32_t nbuf = 256u / (uint32_t)nmax;              // 2 or 1 accumulator buffers
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TS_NSA; ++i) { mbar_init(a_full + 8 * i, 4); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(d_full + 8 * i, 1); mbar_init(d_empty + 8 * i, 16); }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(smem_u32(tmem_slot));
+  for (int i = threadIdx.x; i < p.n_layers * 256; i += blockDim.x) {
+    const int l = i >> 8, n = i & 255;
+    sbias[i] = (p.layer[l].bias && n < p.layer[l].N) ? __ldg(p.layer[l].bias + n) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int L = p.n_layers;
+  const int64_t ntiles = (p.V + TILE_M - 1) / TILE_M;
+
+  if (warp == 0) {
+    // ===================== weight producer (bulk TMA) =====================
+    uint32_t s = 0, ph = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int l = 0; l < L; ++l) {
+        const int N = p.layer[l].N, nch = p.layer[l].K / KC;
+        const uint32_t img_bytes = (uint32_t)N * KC * 4;
+        const uint32_t bytes = p.passes == 3 ? 2 * img_bytes : img_bytes;
+        const float* wsrc = p.layer[l].wpack;
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(b_empty + 8 * s, ph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(b_full + 8 * s, bytes);
+            tma_bulk_g2s(smem_u32(smB + s * b_stage), wsrc + (int64_t)c * 2 * N * KC, bytes, b_full + 8 * s);
+          }
+          __syncwarp();
+          if (++s == nsb) { s = 0; ph ^= 1; }
+        }
+      }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: A from TMEM, B from shared memory =====================
+    const uint32_t smB_u = smem_u32(smB) >> 4;
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, g = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int l = 0; l < L; ++l, ++g) {
+        const int N = p.layer[l].N, nch = p.layer[l].K / KC;
+        const uint32_t idesc = make_idesc_tf32(TILE_M, N);
+        const uint32_t buf = (nbuf == 2) ? (g & 1) : 0, use = (nbuf == 2) ? (g >> 1) : g;
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)nmax;
+        const uint32_t b_lbo = (uint32_t)N * 16;
+        const uint64_t tmplB = make_desc(0, b_lbo, 128);
+        const uint32_t b_img_u = ((uint32_t)N * KC * 4) >> 4, b_ks_u = (2 * b_lbo) >> 4;
+        if (use > 0) {
+          mbar_wait(d_empty + 8 * buf, (use - 1) & 1);
+          tc_fence_after();
+        }
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(a_full + 8 * sa, pa);
+          mbar_wait(b_full + 8 * sb, pb);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_hi0 = tmem_base + TS_ACOL + sa * 32;
+            const uint64_t dbh = tmplB + (smB_u + sb * (b_stage >> 4));
+#pragma unroll
+            for (int ks = 0; ks < KC / 8; ++ks) {
+              const uint32_t a_hi = a_hi0 + ks * 8, a_lo = a_hi + 16;
+              const uint64_t b_h = dbh + ks * b_ks_u;
+              const uint32_t acc = (c | ks) ? 1u : 0u;
+              if (p.passes == 3) {
+                mma_tf32_ts(d_tmem, a_lo, b_h, idesc, acc);
+                mma_tf32_ts(d_tmem, a_hi, b_h + b_img_u, idesc, 1u);
+                mma_tf32_ts(d_tmem, a_hi, b_h, idesc, 1u);
+              } else {
+                mma_tf32_ts(d_tmem, a_hi, b_h, idesc, acc);
+              }
+            }
+            mma_commit(a_empty + 8 * sa);
+            mma_commit(b_empty + 8 * sb);
+            if (c + 1 == nch) mma_commit(d_full + 8 * buf);
+          }
+          __syncwarp();
+          if (++sa == TS_NSA) { sa = 0; pa ^= 1; }
+          if (++sb == nsb) { sb = 0; pb ^= 1; }
+        }
+      }
+  } else {
+    // ===================== workers =====================
+    const int wgi = (warp - 2) >> 2;          // K-chunk class (c % 4) this warpgroup owns
+    const int quarter = warp & 3;             // TMEM lane quarter: this lane owns tile row 32*quarter + lane
+    const int trow = 32 * quarter + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * quarter) << 16);
+    uint32_t ci = 0, g = 0;
+    const int nch0 = p.layer[0].K / KC;
+    const float* rowp[DN_MAX_SRC];
+    bool row_ok = false;
+    auto set_tile = [&](int64_t row0_) {
+      const int64_t rr = row0_ + trow;
+      row_ok = rr < p.V;
+#pragma unroll
+      for (int q = 0; q < DN_MAX_SRC; ++q) rowp[q] = (q < p.src.nsrc) ? p.src.ptr[q] + rr * p.src.ld[q] : nullptr;
+    };
+    auto load_chunk = [&](int c, float4* r) {     // 16 consecutive floats of this lane's own row
+      int k0 = c * KC, s = 0;
+      while (s + 1 < p.src.nsrc && k0 >= p.src.width[s]) { k0 -= p.src.width[s]; ++s; }
+      const float4* base = reinterpret_cast<const float4*>((s == 0 ? rowp[0] : (s == 1 ? rowp[1] : rowp[2])) + k0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = row_ok ? __ldg(base + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    // x = hi + lo -> TMEM stage (hi in columns [0,16), lo in [16,32) of the stage), then hand it to the MMA
+    auto put_chunk = [&](uint32_t cidx, const float* x16) {
+      const uint32_t s = cidx % TS_NSA, ph = (cidx / TS_NSA) & 1;
+      mbar_wait(a_empty + 8 * s, ph ^ 1);
+      tc_fence_after();
+      float hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) split_tf32_fast(x16[j], hi[j], lo[j]);
+      const uint32_t ta = lane_base + TS_ACOL + s * 32;
+      tmem_st16(ta, hi);
+      if (p.passes == 3) tmem_st16(ta + 16, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full + 8 * s);
+    };
+    float4 r[4];
+    if ((int64_t)blockIdx.x < ntiles) {
+      set_tile((int64_t)blockIdx.x * TILE_M);
+      if (wgi < nch0) load_chunk(wgi, r);
+    }
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t row0 = tile * TILE_M;
+      for (int l = 0; l < L; ++l, ++g) {
+        const TcLayer& Lr = p.layer[l];
+        const int nch = Lr.K / KC;
+        if (l == 0) {
+          for (int c = wgi; c < nch; c += 4) {
+            float x16[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { x16[4 * j] = r[j].x; x16[4 * j + 1] = r[j].y; x16[4 * j + 2] = r[j].z; x16[4 * j + 3] = r[j].w; }
+            if (c + 4 < nch) load_chunk(c + 4, r);       // next chunk's loads fly while this one is converted
+            put_chunk(ci + c, x16);
+          }
+          const int64_t nt = tile + gridDim.x;
+          if (nt < ntiles) {
+            set_tile(nt * TILE_M);
+            if (wgi < nch0) load_chunk(wgi, r);
+          }
+        }
+        const uint32_t ci_next = ci + nch;
+        // ---- epilogue of layer l (and operand production for layer l+1)
+        const bool has_next = (l + 1 < L);
+        const int64_t row = row0 + trow;
+        const int nco = Lr.N / KC;
+        const bool has_res = Lr.residual != nullptr;
+        const uint32_t buf = (nbuf == 2) ? (g & 1) : 0, use = (nbuf == 2) ? (g >> 1) : g;
+        auto load_res = [&](int c, float4* q) {
+          const float4* rp = reinterpret_cast<const float4*>(Lr.residual + row * Lr.ld_res + c * KC);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[j] = (row < p.V) ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        float4 res[4];
+        if (has_res && wgi < nco) load_res(wgi, res);
+        const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
+        mbar_wait(d_full + 8 * buf, use & 1);
+        tc_fence_after();
+        const uint32_t d_lane = lane_base + buf * (uint32_t)nmax;
+        for (int c = wgi; c < nco; c += 4) {
+          float v[16];
+          tmem_ld16(d_lane + c * KC, v);
+          const int n0 = c * KC;
+          if (Lr.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(sbias + l * 256 + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = bp[j];
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (Lr.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (Lr.row_scale) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= rs;
+          }
+          if (has_res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
+            }
+            if (c + 4 < nco) load_res(c + 4, res);
+          }
+          if (Lr.out && row < p.V) {
+            float4* op = reinterpret_cast<float4*>(Lr.out + row * Lr.ld_out + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (has_next) put_chunk(ci_next + c, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty + 8 * buf);
+        ci = ci_next;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
 // to_basis, split over V:  partial[cta][k][c] = sum_{v in cta's range} Phi[v][k] * m[v] * x[v][c]
 //   A = Phi^T (M = K_eig rows, padded to 128), B = (m x)^T (N = C rows); reduction dim = v.
 //   Both operands are transposed on the fly: each lane loads a 4(v) x 4(k) block with float4
@@ -650,6 +898,8 @@ bool tc_supported_device() {
                 cudaSuccess ||
             cudaFuncSetAttribute(rows_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+            cudaFuncSetAttribute(rows_chain_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM) !=
+                cudaSuccess ||
             cudaFuncSetAttribute(to_basis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM) !=
                 cudaSuccess) {
           cudaGetLastError();
@@ -754,6 +1004,19 @@ int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers_in, int n_layers, 
     T.out = L.out; T.ld_out = L.ld_out; T.K = L.K; T.N = L.N; T.relu = L.relu;
   }
   const int64_t ntiles = (V + TILE_M - 1) / TILE_M;
+  static int use_ts = -1;
+  if (use_ts < 0) {
+    const char* e = getenv("DN_TC_TS");
+    use_ts = e ? atoi(e) : 2;   // 0: never, 1: always, 2 (default): for chained layers
+  }
+  // measured on B200 (V=200k): MiniMLP chain 301 us (TMEM-A) vs 347 us (smem operands); single layers are a few
+  // microseconds faster with two co-resident smem-operand CTAs per SM
+  if (use_ts == 1 || (use_ts == 2 && n_layers > 1)) {   // activations in TMEM (A operand read from tensor memory), one CTA per SM
+    const int grid1 = (int)(ntiles < g_sm_count ? ntiles : g_sm_count);
+    rows_chain_ts_kernel<<<grid1, TS_THREADS, TS_SMEM, st>>>(p);
+    DN_LAUNCH_CHECK();
+    return DN_OK;
+  }
   const int grid = (int)(ntiles < 2 * g_sm_count ? ntiles : 2 * g_sm_count);
   rows_chain_kernel<<<grid, CHAIN_THREADS, CHAIN_SMEM, st>>>(p);
   DN_LAUNCH_CHECK();
