@@ -463,8 +463,9 @@ int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const
   src_mlp.nsrc = nsrc;
   // one launch packs (hi/lo split + UMMA layout) every weight the tensor-core kernels will stream
   const bool tc = use_tc(engine) && tc_supported_device();
-  const bool tc_front = tc && tc_rows_chain_supported(src_fb, &L[0], 1) == DN_OK &&
-                        (nfront == 1 || tc_rows_chain_supported(src_pq, &L[1], 1) == DN_OK);
+  const bool tc_front = tc && ((nfront == 2 && tc_rows_chain_supported(src_fb, &L[0], 2) == DN_OK) ||
+                               (tc_rows_chain_supported(src_fb, &L[0], 1) == DN_OK &&
+                                (nfront == 1 || tc_rows_chain_supported(src_pq, &L[1], 1) == DN_OK)));
   const bool tc_mlp = tc && tc_rows_chain_supported(src_mlp, &L[nfront], nm) == DN_OK;
   if (tc_front || tc_mlp) {
     DnLayer* first = tc_front ? &L[0] : &L[nfront];
@@ -482,9 +483,14 @@ int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const
   }
   void* tcws = ws.base + ws.off;
   const int64_t tcws_bytes = ws.size - ws.off;
-  if ((rc = run_chain(src_fb, &L[0], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
-  if (nfront == 2)
-    if ((rc = run_chain(src_pq, &L[1], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
+  // from_basis and [P|Q]: one fused two-layer chain on the TMEM-A kernel when it fits, else two launches
+  if (nfront == 2 && tc && tc_rows_chain_supported(src_fb, &L[0], 2) == DN_OK) {
+    if ((rc = run_chain(src_fb, &L[0], 2, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
+  } else {
+    if ((rc = run_chain(src_fb, &L[0], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
+    if (nfront == 2)
+      if ((rc = run_chain(src_pq, &L[1], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
+  }
   // (a4+a5) sparse tangent gradient + complex inner product + tanh   [layers.py:216-226,128-130]
   if (p->with_gradient_features)
     if ((rc = launch_spmm_features(grad, xd, pq, rot, V, C, feat, st))) return rc;

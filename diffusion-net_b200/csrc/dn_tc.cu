@@ -55,6 +55,9 @@ struct TcChainParams {
   int prefetch;   // sources are row-contiguous: bulk-prefetch the next tile into L2
   int64_t V;
   long long* trace;   // optional (tools/trace_chain.py): per-warp (event, clock64) pairs of CTA 0
+  // TMEM plan of the TMEM-A kernel: accumulator column of buffer 0/1, number of buffers, first column and
+  // depth (4 or 8) of the activation ring
+  int acc_col[2], nbuf, a_col0, nsa;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -431,7 +434,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
 // ---------------------------------------------------------------------------------------------
 constexpr int TS_THREADS = 576;
 constexpr int TS_NSA = 8;                    // activation stages in TMEM
-constexpr int TS_ACOL = 256;                 // first TMEM column of the activation ring
 constexpr int TS_BIAS_FLOATS = DN_MAX_LAYERS * 256;
 constexpr int TS_BBYTES = 131072;            // weight ring: 8 stages at N<=128, 4 at N=256
 constexpr int TS_SMEM = TS_BBYTES + TS_BIAS_FLOATS * 4 + 512;
@@ -450,7 +452,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
   const int nmax = p.nmax;
   const uint32_t b_stage = 2u * (uint32_t)nmax * KC * 4;    // hi + lo weight chunk (16 or 32 KiB)
   const uint32_t nsb = TS_BBYTES / b_stage;                 // 8 or 4
-  const uint32_t nbuf = 256u / (uint32_t)nmax;              // 2 or 1 accumulator buffers
+  const uint32_t nbuf = (uint32_t)p.nbuf;                   // 2 or 1 accumulator buffers
+  const uint32_t nsa = (uint32_t)p.nsa, nsa_sh = (p.nsa == 8) ? 3u : 2u;   // activation ring depth (8 or 4)
+  const uint32_t a_col0 = (uint32_t)p.a_col0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
         const int N = p.layer[l].N, nch = p.layer[l].K / KC;
         const uint32_t idesc = make_idesc_tf32(TILE_M, N);
         const uint32_t buf = (nbuf == 2) ? (g & 1) : 0, use = (nbuf == 2) ? (g >> 1) : g;
-        const uint32_t d_tmem = tmem_base + buf * (uint32_t)nmax;
+        const uint32_t d_tmem = tmem_base + (uint32_t)p.acc_col[buf];
         const uint32_t b_lbo = (uint32_t)N * 16;
         const uint64_t tmplB = make_desc(0, b_lbo, 128);
         const uint32_t b_img_u = ((uint32_t)N * KC * 4) >> 4, b_ks_u = (2 * b_lbo) >> 4;
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
           mbar_wait(b_full + 8 * sb, pb);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t a_hi0 = tmem_base + TS_ACOL + sa * 32;
+            const uint32_t a_hi0 = tmem_base + a_col0 + sa * 32;
             const uint64_t dbh = tmplB + (smB_u + sb * (b_stage >> 4));
 #pragma unroll
             for (int ks = 0; ks < KC / 8; ++ks) {
@@ -533,7 +537,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
             if (c + 1 == nch) mma_commit(d_full + 8 * buf);
           }
           __syncwarp();
-          if (++sa == TS_NSA) { sa = 0; pa ^= 1; }
+          if (++sa == nsa) { sa = 0; pa ^= 1; }
           if (++sb == nsb) { sb = 0; pb ^= 1; }
         }
       }
@@ -562,13 +566,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
     };
     // x = hi + lo -> TMEM stage (hi in columns [0,16), lo in [16,32) of the stage), then hand it to the MMA
     auto put_chunk = [&](uint32_t cidx, const float* x16) {
-      const uint32_t s = cidx % TS_NSA, ph = (cidx / TS_NSA) & 1;
+      const uint32_t s = cidx & (nsa - 1), ph = (cidx >> nsa_sh) & 1;
       mbar_wait(a_empty + 8 * s, ph ^ 1);
       tc_fence_after();
       float hi[16], lo[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) split_tf32_fast(x16[j], hi[j], lo[j]);
-      const uint32_t ta = lane_base + TS_ACOL + s * 32;
+      const uint32_t ta = lane_base + a_col0 + s * 32;
       tmem_st16(ta, hi);
       if (p.passes == 3) tmem_st16(ta + 16, lo);
       tmem_st_wait();
@@ -617,7 +621,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
         const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
         mbar_wait(d_full + 8 * buf, use & 1);
         tc_fence_after();
-        const uint32_t d_lane = lane_base + buf * (uint32_t)nmax;
+        const uint32_t d_lane = lane_base + (uint32_t)p.acc_col[buf];
         for (int c = wgi; c < nco; c += 4) {
           float v[16];
           tmem_ld16(d_lane + c * KC, v);
@@ -913,6 +917,11 @@ bool tc_supported_device() {
   return g_tc_ok == 1;
 }
 
+static bool ts_allowed_env() {
+  const char* e = getenv("DN_TC_TS");
+  return !e || atoi(e) != 0;
+}
+
 int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers) {
   if (n_layers < 1 || n_layers > DN_MAX_LAYERS) return DN_ERR_UNSUPPORTED;
   int k0 = 0;
@@ -931,8 +940,10 @@ int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_l
       return DN_ERR_UNSUPPORTED;
     if (L.out && (L.ld_out % 4 || (reinterpret_cast<uintptr_t>(L.out) & 15))) return DN_ERR_UNSUPPORTED;
     if (l > 0 && L.K != layers[l - 1].N) return DN_ERR_UNSUPPORTED;
-    // a 256-wide accumulator fills this CTA's TMEM: no room to ping-pong between chained layers
-    if (L.N > 128 && n_layers > 1) return DN_ERR_UNSUPPORTED;
+    // a 256-wide accumulator cannot ping-pong with another one; the TMEM-A kernel still fits the two-layer
+    // pattern (N0 <= 128 then N1 <= 256: from_basis -> [P|Q]) next to a 4-stage activation ring
+    if (L.N > 128 && n_layers > 1 && !(ts_allowed_env() && n_layers == 2 && l == 1 && layers[0].N <= 128))
+      return DN_ERR_UNSUPPORTED;
   }
   if (!layers[n_layers - 1].out) return DN_ERR_UNSUPPORTED;
   return DN_OK;
@@ -997,6 +1008,10 @@ int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers_in, int n_layers, 
     if (layers[l].N > 128) p.nmax = 256;
   for (int s = 0; s < src.nsrc; ++s)
     if (src.ld[s] != src.width[s]) p.prefetch = 0;
+  // TMEM plan of the TMEM-A kernel
+  p.acc_col[0] = 0; p.acc_col[1] = 128; p.nbuf = 2; p.a_col0 = 256; p.nsa = 8;
+  if (p.nmax == 256 && n_layers == 1) { p.acc_col[1] = 0; p.nbuf = 1; }
+  if (p.nmax == 256 && n_layers == 2) { p.a_col0 = 384; p.nsa = 4; }   // [0,128) | [128,384) | ring [384,512)
   for (int l = 0; l < n_layers; ++l) {
     const DnLayer& L = layers[l];
     TcLayer& T = p.layer[l];
