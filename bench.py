@@ -323,7 +323,7 @@ def main():
             st_mlp = t_ms(lambda: dn.ops.mlp_apply([x, xd, feat], [l.weight for l in lins], [l.bias for l in lins],
                                                    residual=x))
         stages = {"to_basis_ms": st_to, "diffusion_ms": st_diff, "grad_features_ms": st_gf, "mlp_ms": st_mlp}
-        # dominant kernel: the fused MiniMLP chain (rows_chain_kernel); algorithmic work per vertex:
+        # dominant kernel: the fused MiniMLP chain (rows_chain_ts_kernel); algorithmic work per vertex:
         #   flops 10 C^2 (3C->C->C->C), bytes 4*(3C + C) (read x_in,x_diffuse,features; write out)
         C = C_WIDTH
         mlp_flops, mlp_bytes = 10 * C * C * V, 4 * 4 * C * V
@@ -343,12 +343,12 @@ def main():
                     "frac": gbs / pk["hbm_gbs"], "traffic": None}
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` launch (profiles/)
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-                tj = json.load(fh)["rows_chain_kernel#1"]
+                tj = json.load(fh)["rows_chain_ts_kernel#2"]
             roof["traffic"] = (tj["dram_read_mb"] + tj["dram_write_mb"]) * 1e6
             roof["traffic_unit"] = "bytes per launch (algorithmic: {:.0f})".format(mlp_bytes)
         except Exception:
             pass
-        roof.update({"kernel": "rows_chain_kernel (MiniMLP+skip)", "ms": st_mlp, "peak_source": pk["source"],
+        roof.update({"kernel": "rows_chain_ts_kernel (MiniMLP+skip, 3 fused layers)", "ms": st_mlp, "peak_source": pk["source"],
                      "issued_flop_factor": passes,
                      "note": "achieved = algorithmic fp32 flops / CUDA-event time, peak = measured bf16 cuBLAS burst; "
                              "the kernel issues kind::tf32 MMAs (half the bf16 rate), 3 per product in 3xTF32 mode: "
