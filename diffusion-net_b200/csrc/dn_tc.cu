@@ -680,11 +680,11 @@ constexpr int TB_SBO = 144;
 constexpr int TB_LBO = 16 * TB_SBO;          // 16 eight-row groups (128 rows) per k-group
 constexpr int TB_IMG = 4 * TB_LBO;           // 4 k-groups (16 v) : 9216 B
 constexpr int TB_STAGE = 4 * TB_IMG;         // A hi, A lo, B hi, B lo
-constexpr int TB_NOP = 2;                    // operand (UMMA-layout) ring depth
-constexpr int TB_NST = 6;                    // raw TMA staging ring depth
+constexpr int TB_NOP = 4;                    // operand (UMMA-layout) ring depth
+constexpr int TB_NST = 4;                    // raw TMA staging ring depth
 constexpr int TB_RAW_HALF = KC * 128 * 4;    // 16 rows x up to 128 floats
 constexpr int TB_RAW = 2 * TB_RAW_HALF;      // raw Phi rows + raw x rows
-constexpr int TB_THREADS = 320;              // warp0 TMA, warp1 MMA, warps 2..9 converters
+constexpr int TB_THREADS = 576;              // warp0 TMA, warp1 MMA, warps 2..17 converters (two sets of 8)
 constexpr int TB_SMEM = TB_NST * TB_RAW + TB_NOP * TB_STAGE + 1024;
 
 struct TcToBasisParams {
@@ -777,8 +777,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
       __syncwarp();
     }
   } else {
-    // ===== converters: warps 2..5 build A = Phi^T, warps 6..9 build B = (m x)^T; 4 vertices each =====
-    const int w = warp - 2;
+    // ===== converters: two sets of 8 warps alternate chunks (the per-chunk wait->LDS->split->STS->fence->arrive
+    // chain is latency-bound, so two chunks are converted concurrently); inside a set warps 0..3 build
+    // A = Phi^T and warps 4..7 build B = (m x)^T, 4 vertices each =====
+    const int cset = (warp - 2) >> 3;
+    const int w = (warp - 2) & 7;
     const bool isB = w >= 4;
     const int vg = w & 3;
     const int width = isB ? p.C : p.K;
@@ -789,18 +792,18 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
     if (use_mass && nch > 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int64_t v = c_beg * KC + 4 * vg + j;
+        const int64_t v = (c_beg + cset) * KC + 4 * vg + j;
         mnext[j] = (v < p.V) ? __ldg(p.mass + v) : 0.f;
       }
     }
-    for (int64_t c = 0; c < nch; ++c) {
+    for (int64_t c = cset; c < nch; c += 2) {
       const int64_t v0 = (c_beg + c) * KC + 4 * vg;
       float m[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) m[j] = mnext[j];
-      if (use_mass && c + 1 < nch) {
+      if (use_mass && c + 2 < nch) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mnext[j] = (v0 + KC + j < p.V) ? __ldg(p.mass + v0 + KC + j) : 0.f;
+        for (int j = 0; j < 4; ++j) mnext[j] = (v0 + 2 * KC + j < p.V) ? __ldg(p.mass + v0 + 2 * KC + j) : 0.f;
       }
       const uint32_t s = c % TB_NST, ph = (c / TB_NST) & 1;
       mbar_wait(st_full + 8 * s, ph);
@@ -838,7 +841,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
       }
     }
     // ---- epilogue: sum the TMEM accumulators -> partial[cta][k][c]  (warps 2..5 = 4 lane quarters)
-    if (w < 4) {
+    if (cset == 0 && w < 4) {
       float* out = p.partial + (int64_t)blockIdx.x * p.K * p.C;
       const int quarter = warp & 3;
       const int k = 32 * quarter + lane;
