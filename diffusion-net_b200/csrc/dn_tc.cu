@@ -58,6 +58,7 @@ struct TcChainParams {
   // TMEM plan of the TMEM-A kernel: accumulator column of buffer 0/1, number of buffers, first column and
   // depth (4 or 8) of the activation ring
   int acc_col[2], nbuf, a_col0, nsa;
+  int ts_split;   // 1: loader / epilogue warpgroups with a split activation ring; 0: all warpgroups do both
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -453,14 +454,20 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
   const uint32_t b_stage = 2u * (uint32_t)nmax * KC * 4;    // hi + lo weight chunk (16 or 32 KiB)
   const uint32_t nsb = TS_BBYTES / b_stage;                 // 8 or 4
   const uint32_t nbuf = (uint32_t)p.nbuf;                   // 2 or 1 accumulator buffers
-  const uint32_t nsa = (uint32_t)p.nsa, nsa_sh = (p.nsa == 8) ? 3u : 2u;   // activation ring depth (8 or 4)
+  // the activation ring is split in two halves with their own barriers: half 0 holds layer-0 chunks (written by
+  // the loader warps, which may run ahead into the next tile), half 1 the chained-layer chunks (written by the
+  // epilogue warps).  Each half has a single in-order producer stream, which the mbarrier parity protocol needs.
+  // (p.ts_split == 0: one ring, all warpgroups produce in program order.)
+  const bool split = p.ts_split != 0;
+  const uint32_t nsh = split ? (uint32_t)p.nsa / 2 : (uint32_t)p.nsa;           // stages per ring (half)
+  const uint32_t nsh_sh = (nsh == 8) ? 3u : ((nsh == 4) ? 2u : 1u);
   const uint32_t a_col0 = (uint32_t)p.a_col0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < TS_NSA; ++i) { mbar_init(a_full + 8 * i, 4); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < 8; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(d_full + 8 * i, 1); mbar_init(d_empty + 8 * i, 16); }
+    for (int i = 0; i < 2; ++i) { mbar_init(d_full + 8 * i, 1); mbar_init(d_empty + 8 * i, p.ts_split ? 8 : 16); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(smem_u32(tmem_slot));
@@ -498,7 +505,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
   } else if (warp == 1) {
     // ===================== MMA issuer: A from TMEM, B from shared memory =====================
     const uint32_t smB_u = smem_u32(smB) >> 4;
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, g = 0;
+    uint32_t sr[2] = {0, 0}, pr[2] = {0, 0}, sb = 0, pb = 0, g = 0;   // ring half 0: layer-0 chunks, half 1: chained
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
       for (int l = 0; l < L; ++l, ++g) {
         const int N = p.layer[l].N, nch = p.layer[l].K / KC;
@@ -513,7 +520,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
           tc_fence_after();
         }
         for (int c = 0; c < nch; ++c) {
-          mbar_wait(a_full + 8 * sa, pa);
+          const uint32_t hf = (l == 0 || !split) ? 0u : 1u;
+          const uint32_t sa = hf * nsh + sr[hf];
+          mbar_wait(a_full + 8 * sa, pr[hf]);
           mbar_wait(b_full + 8 * sb, pb);
           tc_fence_after();
           if (elect_one()) {
@@ -537,36 +546,24 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
             if (c + 1 == nch) mma_commit(d_full + 8 * buf);
           }
           __syncwarp();
-          if (++sa == nsa) { sa = 0; pa ^= 1; }
+          if (++sr[hf] == nsh) { sr[hf] = 0; pr[hf] ^= 1; }
           if (++sb == nsb) { sb = 0; pb ^= 1; }
         }
       }
   } else {
-    // ===================== workers =====================
-    const int wgi = (warp - 2) >> 2;          // K-chunk class (c % 4) this warpgroup owns
+    // ===================== workers: two LOADER warpgroups + two EPILOGUE warpgroups =====================
+    // Loaders only build layer-0 chunks from HBM and are throttled solely by the activation ring, so while the
+    // MMA works on a tile's last layer (and the epilogue warps drain it) they already stream the next tile in.
+    // Epilogue warps own every accumulator read: bias/ReLU/residual, the output store and the next layer's chunks.
+    const int ww = warp - 2;
+    const bool is_loader = ww < 8;
+    const int par = (ww >> 2) & 1;            // K-chunk parity this warpgroup owns inside its role
     const int quarter = warp & 3;             // TMEM lane quarter: this lane owns tile row 32*quarter + lane
     const int trow = 32 * quarter + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * quarter) << 16);
-    uint32_t ci = 0, g = 0;
-    const int nch0 = p.layer[0].K / KC;
-    const float* rowp[DN_MAX_SRC];
-    bool row_ok = false;
-    auto set_tile = [&](int64_t row0_) {
-      const int64_t rr = row0_ + trow;
-      row_ok = rr < p.V;
-#pragma unroll
-      for (int q = 0; q < DN_MAX_SRC; ++q) rowp[q] = (q < p.src.nsrc) ? p.src.ptr[q] + rr * p.src.ld[q] : nullptr;
-    };
-    auto load_chunk = [&](int c, float4* r) {     // 16 consecutive floats of this lane's own row
-      int k0 = c * KC, s = 0;
-      while (s + 1 < p.src.nsrc && k0 >= p.src.width[s]) { k0 -= p.src.width[s]; ++s; }
-      const float4* base = reinterpret_cast<const float4*>((s == 0 ? rowp[0] : (s == 1 ? rowp[1] : rowp[2])) + k0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) r[j] = row_ok ? __ldg(base + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
     // x = hi + lo -> TMEM stage (hi in columns [0,16), lo in [16,32) of the stage), then hand it to the MMA
-    auto put_chunk = [&](uint32_t cidx, const float* x16) {
-      const uint32_t s = cidx & (nsa - 1), ph = (cidx >> nsa_sh) & 1;
+    auto put_chunk = [&](uint32_t hf, uint32_t idx, const float* x16) {     // idx: running chunk count of that half
+      const uint32_t s = hf * nsh + (idx & (nsh - 1)), ph = (idx >> nsh_sh) & 1;
       mbar_wait(a_empty + 8 * s, ph ^ 1);
       tc_fence_after();
       float hi[16], lo[16];
@@ -580,86 +577,210 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full + 8 * s);
     };
-    float4 r[4];
-    if ((int64_t)blockIdx.x < ntiles) {
-      set_tile((int64_t)blockIdx.x * TILE_M);
-      if (wgi < nch0) load_chunk(wgi, r);
-    }
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t row0 = tile * TILE_M;
-      for (int l = 0; l < L; ++l, ++g) {
-        const TcLayer& Lr = p.layer[l];
-        const int nch = Lr.K / KC;
-        if (l == 0) {
-          for (int c = wgi; c < nch; c += 4) {
-            float x16[16];
+    if (!split) {
+      // ---- unspecialised: all four warpgroups build layer-0 chunks (c % 4) and run the epilogues in program order
+      const int wgi = ww >> 2;
+      const int nch0 = p.layer[0].K / KC;
+      const float* rowp[DN_MAX_SRC];
+      bool row_ok = false;
+      auto set_tile = [&](int64_t row0_) {
+        const int64_t rr = row0_ + trow;
+        row_ok = rr < p.V;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { x16[4 * j] = r[j].x; x16[4 * j + 1] = r[j].y; x16[4 * j + 2] = r[j].z; x16[4 * j + 3] = r[j].w; }
-            if (c + 4 < nch) load_chunk(c + 4, r);       // next chunk's loads fly while this one is converted
-            put_chunk(ci + c, x16);
-          }
-          const int64_t nt = tile + gridDim.x;
-          if (nt < ntiles) {
-            set_tile(nt * TILE_M);
-            if (wgi < nch0) load_chunk(wgi, r);
-          }
-        }
-        const uint32_t ci_next = ci + nch;
-        // ---- epilogue of layer l (and operand production for layer l+1)
-        const bool has_next = (l + 1 < L);
-        const int64_t row = row0 + trow;
-        const int nco = Lr.N / KC;
-        const bool has_res = Lr.residual != nullptr;
-        const uint32_t buf = (nbuf == 2) ? (g & 1) : 0, use = (nbuf == 2) ? (g >> 1) : g;
-        auto load_res = [&](int c, float4* q) {
-          const float4* rp = reinterpret_cast<const float4*>(Lr.residual + row * Lr.ld_res + c * KC);
+        for (int q = 0; q < DN_MAX_SRC; ++q) rowp[q] = (q < p.src.nsrc) ? p.src.ptr[q] + rr * p.src.ld[q] : nullptr;
+      };
+      auto load_chunk = [&](int c, float4* r) {
+        int k0 = c * KC, s = 0;
+        while (s + 1 < p.src.nsrc && k0 >= p.src.width[s]) { k0 -= p.src.width[s]; ++s; }
+        const float4* base = reinterpret_cast<const float4*>((s == 0 ? rowp[0] : (s == 1 ? rowp[1] : rowp[2])) + k0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) q[j] = (row < p.V) ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        };
-        float4 res[4];
-        if (has_res && wgi < nco) load_res(wgi, res);
-        const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
-        mbar_wait(d_full + 8 * buf, use & 1);
-        tc_fence_after();
-        const uint32_t d_lane = lane_base + (uint32_t)p.acc_col[buf];
-        for (int c = wgi; c < nco; c += 4) {
-          float v[16];
-          tmem_ld16(d_lane + c * KC, v);
-          const int n0 = c * KC;
-          if (Lr.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(sbias + l * 256 + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b = bp[j];
-              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        for (int j = 0; j < 4; ++j) r[j] = row_ok ? __ldg(base + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      uint32_t ci = 0, g = 0;
+      float4 r[4];
+      if ((int64_t)blockIdx.x < ntiles) {
+        set_tile((int64_t)blockIdx.x * TILE_M);
+        if (wgi < nch0) load_chunk(wgi, r);
+      }
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * TILE_M;
+        for (int l = 0; l < L; ++l, ++g) {
+          const TcLayer& Lr = p.layer[l];
+          const int nch = Lr.K / KC;
+          if (l == 0) {
+            for (int c = wgi; c < nch; c += 4) {
+              float x16[16];
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) { x16[4 * j] = r[j].x; x16[4 * j + 1] = r[j].y; x16[4 * j + 2] = r[j].z; x16[4 * j + 3] = r[j].w; }
+              if (c + 4 < nch) load_chunk(c + 4, r);       // next chunk's loads fly while this one is converted
+              put_chunk(0u, ci + c, x16);
+            }
+            const int64_t nt = tile + gridDim.x;
+            if (nt < ntiles) {
+              set_tile(nt * TILE_M);
+              if (wgi < nch0) load_chunk(wgi, r);
             }
           }
-          if (Lr.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (Lr.row_scale) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] *= rs;
-          }
-          if (has_res) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
+          const uint32_t ci_next = ci + nch;
+          // ---- epilogue of layer l (and operand production for layer l+1)
+          const bool has_next = (l + 1 < L);
+          const int64_t row = row0 + trow;
+          const int nco = Lr.N / KC;
+          const bool has_res = Lr.residual != nullptr;
+          const uint32_t buf = (nbuf == 2) ? (g & 1) : 0, use = (nbuf == 2) ? (g >> 1) : g;
+          auto load_res = [&](int c, float4* q) {
+            const float4* rp = reinterpret_cast<const float4*>(Lr.residual + row * Lr.ld_res + c * KC);
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) q[j] = (row < p.V) ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          };
+          float4 res[4];
+          if (has_res && wgi < nco) load_res(wgi, res);
+          const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
+          mbar_wait(d_full + 8 * buf, use & 1);
+          tc_fence_after();
+          const uint32_t d_lane = lane_base + (uint32_t)p.acc_col[buf];
+          for (int c = wgi; c < nco; c += 4) {
+            float v[16];
+            tmem_ld16(d_lane + c * KC, v);
+            const int n0 = c * KC;
+            if (Lr.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(sbias + l * 256 + n0);
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 b = bp[j];
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
             }
-            if (c + 4 < nco) load_res(c + 4, res);
+            if (Lr.relu) {
+  #pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (Lr.row_scale) {
+  #pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] *= rs;
+            }
+            if (has_res) {
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
+              }
+              if (c + 4 < nco) load_res(c + 4, res);
+            }
+            if (Lr.out && row < p.V) {
+              float4* op = reinterpret_cast<float4*>(Lr.out + row * Lr.ld_out + n0);
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (has_next) put_chunk(0u, ci_next + c, v);
           }
-          if (Lr.out && row < p.V) {
-            float4* op = reinterpret_cast<float4*>(Lr.out + row * Lr.ld_out + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (has_next) put_chunk(ci_next + c, v);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d_empty + 8 * buf);
+          ci = ci_next;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(d_empty + 8 * buf);
-        ci = ci_next;
+      }
+    } else if (is_loader) {
+      const int nch0 = p.layer[0].K / KC;
+      const float* rowp[DN_MAX_SRC];
+      bool row_ok = false;
+      auto set_tile = [&](int64_t row0_) {
+        const int64_t rr = row0_ + trow;
+        row_ok = rr < p.V;
+#pragma unroll
+        for (int q = 0; q < DN_MAX_SRC; ++q) rowp[q] = (q < p.src.nsrc) ? p.src.ptr[q] + rr * p.src.ld[q] : nullptr;
+      };
+      auto load_chunk = [&](int c, float4* r) {     // 16 consecutive floats of this lane's own row
+        int k0 = c * KC, s = 0;
+        while (s + 1 < p.src.nsrc && k0 >= p.src.width[s]) { k0 -= p.src.width[s]; ++s; }
+        const float4* base = reinterpret_cast<const float4*>((s == 0 ? rowp[0] : (s == 1 ? rowp[1] : rowp[2])) + k0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = row_ok ? __ldg(base + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto unpack = [&](const float4* r, float* x16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { x16[4 * j] = r[j].x; x16[4 * j + 1] = r[j].y; x16[4 * j + 2] = r[j].z; x16[4 * j + 3] = r[j].w; }
+      };
+      float4 r0[4], r1[4];                      // two chunks of this warpgroup in flight
+      uint32_t tbase = 0;                       // running count of layer-0 chunks before this tile
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tbase += (uint32_t)nch0) {
+        set_tile(tile * TILE_M);
+        if (par < nch0) load_chunk(par, r0);
+        if (par + 2 < nch0) load_chunk(par + 2, r1);
+        int c = par;
+        while (c < nch0) {
+          float x16[16];
+          unpack(r0, x16);
+          if (c + 4 < nch0) load_chunk(c + 4, r0);
+          put_chunk(0u, tbase + c, x16);
+          c += 2;
+          if (c >= nch0) break;
+          unpack(r1, x16);
+          if (c + 4 < nch0) load_chunk(c + 4, r1);
+          put_chunk(0u, tbase + c, x16);
+          c += 2;
+        }
+      }
+    } else {
+      uint32_t ci = 0, g = 0;                   // ci: running count of chained-layer chunks
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * TILE_M;
+        for (int l = 0; l < L; ++l, ++g) {
+          const TcLayer& Lr = p.layer[l];
+          const bool has_next = (l + 1 < L);
+          const int64_t row = row0 + trow;
+          const int nco = Lr.N / KC;
+          const bool has_res = Lr.residual != nullptr;
+          const uint32_t buf = (nbuf == 2) ? (g & 1) : 0, use = (nbuf == 2) ? (g >> 1) : g;
+          auto load_res = [&](int c, float4* q) {
+            const float4* rp = reinterpret_cast<const float4*>(Lr.residual + row * Lr.ld_res + c * KC);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) q[j] = (row < p.V) ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          };
+          float4 res[4];
+          if (has_res && par < nco) load_res(par, res);
+          const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
+          mbar_wait(d_full + 8 * buf, use & 1);
+          tc_fence_after();
+          const uint32_t d_lane = lane_base + (uint32_t)p.acc_col[buf];
+          for (int c = par; c < nco; c += 2) {
+            float v[16];
+            tmem_ld16(d_lane + c * KC, v);
+            const int n0 = c * KC;
+            if (Lr.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(sbias + l * 256 + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 b = bp[j];
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
+            }
+            if (Lr.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (Lr.row_scale) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] *= rs;
+            }
+            if (has_res) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
+              }
+              if (c + 2 < nco) load_res(c + 2, res);
+            }
+            if (Lr.out && row < p.V) {
+              float4* op = reinterpret_cast<float4*>(Lr.out + row * Lr.ld_out + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (has_next) put_chunk(1u, ci + c, v);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d_empty + 8 * buf);
+          if (has_next) ci += (uint32_t)nco;          // layer l+1 consumed N_l / KC chained chunks
+        }
       }
     }
   }
@@ -1015,6 +1136,16 @@ int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers_in, int n_layers, 
   p.acc_col[0] = 0; p.acc_col[1] = 128; p.nbuf = 2; p.a_col0 = 256; p.nsa = 8;
   if (p.nmax == 256 && n_layers == 1) { p.acc_col[1] = 0; p.nbuf = 1; }
   if (p.nmax == 256 && n_layers == 2) { p.a_col0 = 384; p.nsa = 4; }   // [0,128) | [128,384) | ring [384,512)
+  {
+    // measured (V=200k): role specialisation wins on the 2-layer from_basis+[P|Q] chain (196 -> 167 us: few
+    // layer-0 chunks, heavy epilogues) and loses on the MiniMLP (270 -> 280 us: 24 layer-0 chunks per tile)
+    static int split_env = -2;
+    if (split_env == -2) {
+      const char* e = getenv("DN_TC_SPLIT");
+      split_env = e ? atoi(e) : -1;
+    }
+    p.ts_split = split_env >= 0 ? split_env : (n_layers == 2 ? 1 : 0);
+  }
   for (int l = 0; l < n_layers; ++l) {
     const DnLayer& L = layers[l];
     TcLayer& T = p.layer[l];
