@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
   } else if (warp == 1) {
     // ===================== MMA issuer: A from TMEM, B from shared memory =====================
     const uint32_t smB_u = smem_u32(smB) >> 4;
-    uint32_t sr[2] = {0, 0}, pr[2] = {0, 0}, sb = 0, pb = 0, g = 0;   // ring half 0: layer-0 chunks, half 1: chained
+    uint32_t s0 = 0, p0 = 0, s1 = 0, p1 = 0, sb = 0, pb = 0, g = 0;   // ring half 0: layer-0 chunks, half 1: chained
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
       for (int l = 0; l < L; ++l, ++g) {
         const int N = p.layer[l].N, nch = p.layer[l].K / KC;
@@ -521,8 +521,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
         }
         for (int c = 0; c < nch; ++c) {
           const uint32_t hf = (l == 0 || !split) ? 0u : 1u;
-          const uint32_t sa = hf * nsh + sr[hf];
-          mbar_wait(a_full + 8 * sa, pr[hf]);
+          const uint32_t sa = hf ? nsh + s1 : s0;
+          mbar_wait(a_full + 8 * sa, hf ? p1 : p0);
           mbar_wait(b_full + 8 * sb, pb);
           tc_fence_after();
           if (elect_one()) {
@@ -546,7 +546,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
             if (c + 1 == nch) mma_commit(d_full + 8 * buf);
           }
           __syncwarp();
-          if (++sr[hf] == nsh) { sr[hf] = 0; pr[hf] ^= 1; }
+          if (hf) { if (++s1 == nsh) { s1 = 0; p1 ^= 1; } }
+          else    { if (++s0 == nsh) { s0 = 0; p0 ^= 1; } }
           if (++sb == nsb) { sb = 0; pb ^= 1; }
         }
       }
