@@ -323,3 +323,61 @@ def test_graphed_net_and_streamed_forward(dn):
     for t in tickets:
         assert torch.equal(pipe.result(t), refs[0].cpu())
     assert pipe.h2d_bytes == 3 * sum(v.numel() * v.element_size() for v in host.values())
+
+
+def test_training_mode_dropout_matches_manual_masks(dn):
+    """MiniMLP in train() mode: Dropout(p=.5) after each hidden ReLU (layers.py:143-147).  The masks come from
+    torch's generator, so re-seeding reproduces them; forward and all gradients must match a plain-torch fp64
+    evaluation with the same masks."""
+    dn.set_engine("tc3x")
+    V, C = 300, 32
+    g = torch.Generator().manual_seed(3)
+    mlp = dn.MiniMLP([3 * C, C, C, C], dropout=True).cuda().train()
+    x = torch.randn(V, 3 * C, generator=g).cuda().requires_grad_(True)
+    R = torch.randn(V, C, generator=g).cuda()
+    torch.manual_seed(1234)
+    y = mlp(x)
+    (y * R).sum().backward()
+    # replay the mask draws (same order/shapes as ops.MLPFn.forward)
+    torch.manual_seed(1234)
+    masks = [torch.empty(V, C, device="cuda").bernoulli_(0.5).mul_(2.0) for _ in range(2)]
+    lins = mlp.linears()
+    xr = x.detach().double().requires_grad_(True)
+    ws = [l.weight.detach().double().requires_grad_(True) for l in lins]
+    bs = [l.bias.detach().double().requires_grad_(True) for l in lins]
+    h = xr
+    for i in range(3):
+        h = h @ ws[i].t() + bs[i]
+        if i < 2:
+            h = torch.relu(h) * masks[i].double()
+    (h * R.double()).sum().backward()
+    assert O.rel_err(y.detach().cpu().numpy(), h.detach().cpu().numpy()) < 1e-5
+    assert O.rel_err(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 2e-5
+    for i, l in enumerate(lins):
+        assert O.rel_err(l.weight.grad.cpu().numpy(), ws[i].grad.cpu().numpy()) < 5e-5
+        assert O.rel_err(l.bias.grad.cpu().numpy(), bs[i].grad.cpu().numpy()) < 5e-5
+
+
+def test_net_training_step_and_gradient_allreduce(dn):
+    """One optimiser step of a 2-block net on two meshes with gradients accumulated and averaged through
+    dist.allreduce_gradients (world size 1 here; the collective itself is covered by the gloo test)."""
+    dn.set_engine("tc3x")
+    net = dn.DiffusionNet(C_in=3, C_out=4, C_width=32, N_block=2, dropout=True).cuda().train()
+    with torch.no_grad():
+        for n_, p_ in net.named_parameters():
+            if n_.endswith("diffusion_time"):
+                p_.uniform_(1e-3, 0.3)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    before = [p_.detach().clone() for p_ in net.parameters()]
+    opt.zero_grad()
+    for i in range(2):
+        mass, L, evals, evecs, gX, gY = dn.synthetic.structural_operators(14 + i, 16, 32, seed=i, device="cuda")
+        x = torch.randn((14 + i) * 16, 3, generator=torch.Generator().manual_seed(i)).cuda()
+        out = net(x, mass, evals=evals, evecs=evecs, gradX=gX, gradY=gY)
+        target = torch.randint(0, 4, (out.shape[0],), generator=torch.Generator().manual_seed(10 + i)).cuda()
+        torch.nn.functional.cross_entropy(out, target).backward()
+    dn.dist.allreduce_gradients(list(net.parameters()), n_global_meshes=2)
+    assert all(p_.grad is not None and torch.isfinite(p_.grad).all() for p_ in net.parameters())
+    opt.step()
+    assert any(not torch.equal(a, b) for a, b in zip(before, [p_.detach() for p_ in net.parameters()]))
+    assert float(min(b.diffusion.diffusion_time.min() for b in net.blocks)) >= 0.0
