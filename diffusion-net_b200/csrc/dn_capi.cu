@@ -128,6 +128,23 @@ int dn_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* vx, c
   return launch_csr_from_coo(rows, cols, vx, vy, nnz, V, rowptr, colidx, vals, (cudaStream_t)stream);
 }
 
+int dn_csr_transpose(const dn_csr* in, int64_t V, int32_t* rowptr_out, int32_t* colidx_out, float* vals_out,
+                     void* workspace, int64_t ws_bytes, dn_stream_t stream) {
+  if (!in || V < 0 || in->nnz < 0 || !rowptr_out || (in->nnz > 0 && (!in->rowptr || !in->colidx || !in->vals ||
+                                                                        !colidx_out || !vals_out)))
+    return DN_ERR_INVALID_ARGUMENT;
+  if (in->nnz >= (1ll << 31) || V >= (1ll << 31) - 1) return DN_ERR_UNSUPPORTED;
+  if (in->nnz > 0 && (!workspace || ws_bytes < (int64_t)sizeof(int32_t) * V)) return DN_ERR_WORKSPACE;
+  return launch_csr_transpose(in, V, rowptr_out, colidx_out, vals_out, (int32_t*)workspace, (cudaStream_t)stream);
+}
+
+int dn_compute_hks(const float* evals, const float* evecs, const float* scales, int64_t V, int K, int S, float* out,
+                   dn_stream_t stream) {
+  if (V < 0 || K <= 0 || S < 0 || ((V > 0 && S > 0) && (!evals || !evecs || !scales || !out)))
+    return DN_ERR_INVALID_ARGUMENT;
+  return launch_compute_hks(evals, evecs, scales, V, K, S, out, (cudaStream_t)stream);
+}
+
 int dn_to_basis(const float* values, const float* basis, const float* massvec, int64_t V, int K, int C, float* out,
                 void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream) {
   if (!values || !basis || !out || V < 0 || K <= 0 || C <= 0) return DN_ERR_INVALID_ARGUMENT;

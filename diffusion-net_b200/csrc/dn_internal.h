@@ -71,6 +71,10 @@ int launch_spectral_scale(const float* partial, int P, const float* evals, float
 int launch_reduce_partials(const float* partial, int P, int64_t n, float* out, cudaStream_t st);
 int launch_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* vx, const float* vy,
                         int64_t nnz, int64_t V, int32_t* rowptr, int32_t* colidx, float* vals, cudaStream_t st);
+int launch_compute_hks(const float* evals, const float* evecs, const float* scales, int64_t V, int K, int S,
+                       float* out, cudaStream_t st);
+int launch_csr_transpose(const dn_csr* in, int64_t V, int32_t* rowptr_t, int32_t* colidx_t, float* vals_t,
+                         int32_t* cursor, cudaStream_t st);
 int launch_grad_spmm_pair(const dn_csr* g, const float* x, int64_t V, int C, float* out_vc2, cudaStream_t st);
 // R-order fused features: feat = tanh(gX*Bre + gY*Bim) from gathers of xd, P, Q (pq = [P|Q], ld 2C or C).
 int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int rotations, int64_t V, int C,

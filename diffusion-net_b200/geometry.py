@@ -1,7 +1,13 @@
-"""``to_basis`` / ``from_basis`` with the reference signatures (geometry.py:572-598), running the
-hand-written kernels.  Batched (B,V,*) or single-mesh (V,*) inputs, as the reference accepts."""
+"""The pieces of the reference's ``geometry`` module that sit either side of the block: ``to_basis`` / ``from_basis``
+(geometry.py:572-598), heat-kernel-signature features (geometry.py:600-633) and the READ side of the operator
+cache (geometry.py:426-519) -- all with the reference signatures, all running the hand-written kernels.
+Batched (B,V,*) or single-mesh (V,*) inputs, as the reference accepts."""
 from __future__ import annotations
 
+import hashlib
+import os
+
+import numpy as np
 import torch
 
 from . import ops
@@ -21,3 +27,122 @@ def from_basis(values, basis):
     if values.dim() == 2:
         return ops.from_basis_raw(values, basis)
     return torch.stack([ops.from_basis_raw(values[b], basis[b]) for b in range(values.shape[0])], 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# heat kernel signatures (input features of every experiment that passes --input_features=hks)
+# ------------------------------------------------------------------------------------------------
+def compute_hks(evals, evecs, scales):
+    """(K),(V,K),(S) -> (V,S) or batched (B,K),(B,V,K),(B,S) -> (B,V,S):
+    ``sum_k exp(-evals[k]*scales[s]) * evecs[v,k]^2`` (geometry.py:600-628).  One streaming pass over ``evecs``;
+    the reference materialises a (B,V,S,K) tensor."""
+    if evals.dim() == 1:
+        return ops.compute_hks_raw(evals, evecs, scales)
+    return torch.stack([ops.compute_hks_raw(evals[b], evecs[b], scales[b]) for b in range(evals.shape[0])], 0)
+
+
+def compute_hks_autoscale(evals, evecs, count):
+    """geometry.py:630-633: ``count`` log-spaced scales in [1e-2, 1]."""
+    scales = torch.logspace(-2, 0., steps=count, device=evals.device, dtype=evals.dtype)
+    return compute_hks(evals, evecs, scales)
+
+
+# ------------------------------------------------------------------------------------------------
+# operator cache -> device  (the read side of geometry.py:426-519; construction itself is out of scope)
+# ------------------------------------------------------------------------------------------------
+def hash_arrays(arrs):
+    """utils.py:71-76 -- the cache file name is sha1(verts bytes, faces bytes)."""
+    h = hashlib.sha1()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).view(np.uint8))
+    return h.hexdigest()
+
+
+def _to_np(t):
+    return t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+
+
+def _coo_from_csc(npz, prefix, device, dtype):
+    """A scipy-CSC triple of the cache file as the coalesced COO tensor the reference returns (utils.py:50-55)."""
+    indptr, indices = npz[prefix + "_indptr"], npz[prefix + "_indices"]
+    n = int(npz[prefix + "_shape"][0])
+    cols = torch.repeat_interleave(torch.arange(n), torch.as_tensor(np.diff(indptr).astype(np.int64)))
+    idx = torch.stack((torch.as_tensor(indices.astype(np.int64)), cols), 0)
+    val = torch.as_tensor(npz[prefix + "_data"].astype(np.float32))
+    return torch.sparse_coo_tensor(idx, val, (n, n)).coalesce().to(device=device, dtype=dtype)
+
+
+def load_operators_npz(path_or_npz, k_eig=None, device="cuda", dtype=torch.float32):
+    """One cache entry (the ``np.savez`` of geometry.py:548-568) -> the reference's operator tuple
+    ``(frames, mass, L, evals, evecs, gradX, gradY)`` resident on ``device``.
+
+    gradX/gradY come back as the same coalesced COO tensors the reference returns, so they can be passed to the
+    layers unchanged -- but their kernel-side form (shared-pattern int32 CSR + transposed CSR) is built here directly
+    from the file's CSC arrays and registered against those tensors, so the first forward does no conversion."""
+    npz = np.load(path_or_npz, allow_pickle=True) if isinstance(path_or_npz, (str, os.PathLike)) else path_or_npz
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("diffusion_net_b200 keeps operators on CUDA devices only (no CPU path); got {}".format(device))
+    k_have = int(npz["k_eig"].item())
+    k_eig = k_have if k_eig is None else int(k_eig)
+    if k_eig > k_have:
+        raise ValueError("cache entry holds {} eigenpairs, {} requested".format(k_have, k_eig))
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
+    frames, mass = to(npz["frames"]), to(npz["mass"])
+    evals, evecs = to(npz["evals"][:k_eig]), to(npz["evecs"][:, :k_eig])
+    L = _coo_from_csc(npz, "L", device, dtype)
+    V = int(npz["gradX_shape"][0])
+    same = (np.array_equal(npz["gradX_indptr"], npz["gradY_indptr"])
+            and np.array_equal(npz["gradX_indices"], npz["gradY_indices"]))
+    if same and dtype == torch.float32:
+        gops = ops.GradOperators.from_csc(V, npz["gradX_indptr"], npz["gradX_indices"], npz["gradX_data"],
+                                          npz["gradY_data"], device)
+        gradX, gradY = gops.to_sparse_coo()
+        ops.register_prepared(gradX, gradY, gops)
+    else:  # distinct patterns (never produced by geometry.py:381-382, but legal): generic path at first use
+        gradX, gradY = _coo_from_csc(npz, "gradX", device, dtype), _coo_from_csc(npz, "gradY", device, dtype)
+    return frames, mass, L, evals, evecs, gradX, gradY
+
+
+def find_cached_operators(verts, faces, k_eig, op_cache_dir):
+    """The cache probe of geometry.py:447-492: returns the opened npz of the matching entry or None."""
+    verts_np, faces_np = _to_np(verts), _to_np(faces)
+    key = hash_arrays((verts_np, faces_np))
+    i = 0
+    while True:
+        path = os.path.join(op_cache_dir, "{}_{}.npz".format(key, i))
+        try:
+            npz = np.load(path, allow_pickle=True)
+        except FileNotFoundError:
+            return None
+        if not (np.array_equal(verts_np, npz["verts"]) and np.array_equal(faces_np, npz["faces"])):
+            i += 1                       # hash collision: next bucket (geometry.py:470-473)
+            continue
+        if int(npz["k_eig"].item()) < k_eig or "L_data" not in npz:
+            return None                  # the reference would rebuild such an entry (geometry.py:482-490)
+        return npz
+
+
+def get_operators(verts, faces, k_eig=128, op_cache_dir=None, normals=None, overwrite_cache=False, device=None):
+    """``geometry.get_operators`` (geometry.py:426) for a POPULATED cache: same arguments, same file naming, same
+    returned tuple.  ``device`` (extra) places the operators directly on a GPU; default = ``verts.device``.
+    Building operators (robust-laplacian / eigsh / build_grad, geometry.py:275-393) is out of this framework's
+    scope: a cache miss raises instead of computing."""
+    verts_np = _to_np(verts)
+    if np.isnan(verts_np).any():
+        raise RuntimeError("tried to construct operators from NaN verts")
+    device = torch.device(device) if device is not None else verts.device
+    npz = None
+    if op_cache_dir is not None and not overwrite_cache:
+        npz = find_cached_operators(verts, faces, k_eig, op_cache_dir)
+    if npz is None:
+        raise NotImplementedError(
+            "no usable cache entry for this mesh in {!r}: operator construction is outside the B200 hot path -- "
+            "populate the cache with the reference's get_operators()".format(op_cache_dir))
+    return load_operators_npz(npz, k_eig=k_eig, device=device, dtype=verts.dtype)
+
+
+def get_all_operators(verts_list, faces_list, k_eig, op_cache_dir=None, normals=None, device=None):
+    """geometry.py:395-424: seven parallel lists."""
+    outs = [get_operators(v, f, k_eig, op_cache_dir, device=device) for v, f in zip(verts_list, faces_list)]
+    return tuple([o[i] for o in outs] for i in range(7))

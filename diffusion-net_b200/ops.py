@@ -105,6 +105,47 @@ class GradOperators:
         st = _lib.dn_csr(rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(), self.nnz)
         return (st, rowptr, colidx, vals)   # keep the tensors alive next to the struct
 
+    @classmethod
+    def from_csc(cls, V, indptr, indices, data_x, data_y, device):
+        """Straight from the reference's on-disk cache (scipy CSC arrays, geometry.py:548-568): the CSC arrays ARE
+        the transposed CSR the backward pass needs; the forward CSR comes from one ``dn_csr_transpose`` call.
+        No COO expansion, no coalesce, no int64 indices.  ``data_x``/``data_y`` share (indptr, indices)."""
+        self = cls.__new__(cls)
+        self.V, self.device = int(V), torch.device(device)
+        dev = self.device
+        rowptr_t = torch.as_tensor(indptr, dtype=torch.int32).to(dev)
+        self.nnz = int(len(indices))
+        colidx_t = torch.as_tensor(indices, dtype=torch.int32).to(dev) if self.nnz else \
+            torch.empty(1, dtype=torch.int32, device=dev)
+        vals_t = torch.empty(2 * max(self.nnz, 1), dtype=torch.float32, device=dev)
+        if self.nnz:
+            vals_t[0:2 * self.nnz:2] = torch.as_tensor(data_x, dtype=torch.float32).to(dev)
+            vals_t[1:2 * self.nnz:2] = torch.as_tensor(data_y, dtype=torch.float32).to(dev)
+        st_t = _lib.dn_csr(rowptr_t.data_ptr(), colidx_t.data_ptr(), vals_t.data_ptr(), self.nnz)
+        self._csr_t = (st_t, rowptr_t, colidx_t, vals_t)
+        rowptr = torch.empty(self.V + 1, dtype=torch.int32, device=dev)
+        colidx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+        vals = torch.empty(2 * max(self.nnz, 1), dtype=torch.float32, device=dev)
+        scratch = torch.empty(max(self.V, 1), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().dn_csr_transpose(C.byref(st_t), self.V, rowptr.data_ptr(), colidx.data_ptr(),
+                                                    vals.data_ptr(), scratch.data_ptr(), 4 * scratch.numel(),
+                                                    _stream()), "dn_csr_transpose")
+        self.csr = (_lib.dn_csr(rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(), self.nnz),
+                    rowptr, colidx, vals)
+        self._coo = None
+        return self
+
+    def to_sparse_coo(self):
+        """(gradX, gradY) as the coalesced int64 COO tensors the reference hands around (utils.py:50-55), built from
+        the forward CSR (index plumbing only; rows are sorted and unique, so no coalesce pass is needed)."""
+        _, rowptr, colidx, vals = self.csr
+        counts = (rowptr[1:] - rowptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(self.V, device=self.device), counts)
+        idx = torch.stack((rows, colidx[:self.nnz].long()), 0)
+        mk = lambda v: torch.sparse_coo_tensor(idx, v.contiguous(), (self.V, self.V), is_coalesced=True)
+        return mk(vals[0:2 * self.nnz:2]), mk(vals[1:2 * self.nnz:2])
+
     @property
     def csr_t(self):
         """CSR of the transposed pattern (backward pass); index sort is prep-time plumbing."""
@@ -119,6 +160,19 @@ class GradOperators:
 _prep_cache = {}
 
 
+_prep_sweep_at = 256
+
+
+def _sweep_prep_cache():
+    """Drop entries whose sparse tensors died.  Live entries are never evicted: a dataset keeps its operator
+    tensors for the whole run (SURVEY.md 8b 'Ownership') and their CSR must stay resident with them."""
+    global _prep_sweep_at
+    if len(_prep_cache) > _prep_sweep_at:
+        for k in [k for k, v in _prep_cache.items() if v[0]() is None or v[1]() is None]:
+            del _prep_cache[k]
+        _prep_sweep_at = max(256, 2 * len(_prep_cache))
+
+
 def prepare_operators(gradX, gradY):
     """Memoised on the identity (+ version) of the user's sparse tensors: the reference reuses the
     same operator tensors across blocks and epochs (SURVEY.md section 8b 'Ownership')."""
@@ -129,13 +183,17 @@ def prepare_operators(gradX, gradY):
         if rx() is gradX and ry() is gradY and ver == (gradX._version, gradY._version):
             return ops
     ops = GradOperators(gradX, gradY)
-    if len(_prep_cache) > 256:
-        for k in [k for k, v in _prep_cache.items() if v[0]() is None or v[1]() is None]:
-            del _prep_cache[k]
-        if len(_prep_cache) > 256:
-            _prep_cache.clear()
+    _sweep_prep_cache()
     _prep_cache[key] = (weakref.ref(gradX), weakref.ref(gradY), (gradX._version, gradY._version), ops)
     return ops
+
+
+def register_prepared(gradX, gradY, ops):
+    """Attach an already-built GradOperators to the sparse tensors a caller will pass to the layers
+    (geometry.get_operators builds the CSR straight from the cache file)."""
+    _prep_cache[(id(gradX), id(gradY))] = (weakref.ref(gradX), weakref.ref(gradY),
+                                           (gradX._version, gradY._version), ops)
+    _sweep_prep_cache()
 
 
 def prepare_operators_batched(gradX, gradY):
@@ -176,6 +234,20 @@ def from_basis_raw(values, basis):
     ws = workspace(V, K, Cc, values.device)
     _lib.check(_lib.load().dn_from_basis(values.data_ptr(), basis.data_ptr(), None, V, K, Cc, out.data_ptr(),
                                          ws.data_ptr(), ws.numel(), _engine, _stream()), "dn_from_basis")
+    return out
+
+
+def compute_hks_raw(evals, evecs, scales):
+    _require_cuda(evals, evecs, scales)
+    evals, evecs, scales = _f32c(evals), _f32c(evecs), _f32c(scales)
+    V, K = evecs.shape
+    if evals.shape != (K,) or scales.dim() != 1:
+        raise ValueError("compute_hks expects evals (K), evecs (V,K), scales (S)")
+    S = scales.shape[0]
+    out = torch.empty(V, S, dtype=torch.float32, device=evecs.device)
+    with torch.cuda.device(evecs.device):
+        _lib.check(_lib.load().dn_compute_hks(evals.data_ptr(), evecs.data_ptr(), scales.data_ptr(), V, K, S,
+                                              out.data_ptr(), _stream()), "dn_compute_hks")
     return out
 
 

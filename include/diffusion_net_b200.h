@@ -88,6 +88,17 @@ int dn_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* vx, c
                     int64_t nnz, int64_t V, int32_t* rowptr, int32_t* colidx, float* vals,
                     dn_stream_t stream);
 
+/* Operator prep from the reference's on-disk cache (geometry.py:548-568 stores gradX/gradY as scipy CSC; the
+ * read side is geometry.py:494-519): a CSC matrix is the CSR of its transpose, so the cache arrays are `in`
+ * verbatim and this call produces the forward CSR (columns sorted inside every row, deterministic).
+ * `in` and the outputs describe square V x V matrices; workspace needs 4*V bytes. */
+int dn_csr_transpose(const dn_csr* in, int64_t V, int32_t* rowptr_out, int32_t* colidx_out,
+                     float* vals_out, void* workspace, int64_t ws_bytes, dn_stream_t stream);
+
+/* geometry.py:600-628 compute_hks: out(V,S)[v,s] = sum_k exp(-evals[k]*scales[s]) * evecs(V,K)[v,k]^2. */
+int dn_compute_hks(const float* evals, const float* evecs, const float* scales, int64_t V, int K,
+                   int S, float* out, dn_stream_t stream);
+
 /* geometry.py:572-583 to_basis: out(K,C) = basis(V,K)^T @ (values(V,C) * massvec(V)[:,None]).
  * massvec may be NULL (no weighting; used by the backward pass). */
 int dn_to_basis(const float* values, const float* basis, const float* massvec, int64_t V, int K,

@@ -12,6 +12,8 @@ container: ``oracle/make_golden.py`` imports ``/root/reference/src/diffusion_net
 (with the two absent native deps stubbed; they are not on this path), runs it on
 seeded inputs and commits the inputs + fp32/fp64 outputs under ``tests/golden/``.
 ``tests/test_oracle.py`` checks every function below against those fixtures.
+The data-side neighbours of the path (HKS features, the operator-cache reader) are pinned
+the same way by ``oracle/make_golden_geom.py`` -> ``tests/golden/geom_small.npz`` + ``tests/golden/op_cache/``.
 
 Every function works in the dtype of its inputs (float32 reproduces the
 reference arithmetic order with numpy kernels; float64 is the gold standard the
@@ -26,7 +28,8 @@ import scipy.sparse as sp
 __all__ = [
     "to_basis", "from_basis", "learned_time_diffusion", "grad_spmm",
     "spatial_gradient_features", "mini_mlp", "diffusion_net_block",
-    "diffusion_net", "coo_to_csr", "rel_err",
+    "diffusion_net", "coo_to_csr", "rel_err", "compute_hks", "hks_autoscale_scales", "cache_key",
+    "read_operator_cache",
 ]
 
 
@@ -172,3 +175,37 @@ def diffusion_net(x_in, mass, evals, evecs, gradX, gradY, params, n_block,
     if outputs_at == "global_mean":                                             # :393-397
         return (x * mass[:, None]).sum(axis=0) / mass.sum()
     raise ValueError("invalid setting for outputs_at")
+
+
+# ------------------------------------------------------------------------------------------------
+# data-side neighbours of the block
+# ------------------------------------------------------------------------------------------------
+def compute_hks(evals, evecs, scales):
+    """geometry.py:600-628: (K),(V,K),(S) -> (V,S), ``sum_k exp(-evals[k] scales[s]) evecs[v,k]^2``."""
+    power_coefs = np.exp(-evals[None, :] * scales[:, None])                    # :619  (S,K)
+    return (evecs * evecs) @ power_coefs.T                                     # :620-622 (the "could be a matmul")
+
+
+def hks_autoscale_scales(count, dtype=np.float32):
+    """geometry.py:632: ``torch.logspace(-2, 0, steps=count)``."""
+    return np.logspace(-2.0, 0.0, num=count).astype(dtype)
+
+
+def cache_key(verts, faces):
+    """utils.py:71-76 via geometry.py:450: sha1 over the raw bytes of verts then faces."""
+    import hashlib
+    h = hashlib.sha1()
+    for a in (verts, faces):
+        h.update(np.ascontiguousarray(a).view(np.uint8))
+    return h.hexdigest()
+
+
+def read_operator_cache(npz, k_eig):
+    """geometry.py:494-519 (the cache-hit branch): CSC triples -> scipy matrices, spectrum truncated to k_eig.
+    Returns (frames, mass, L, evals, evecs, gradX, gradY) with the sparse ones as scipy CSR."""
+    def mat(prefix):                                                           # :494-500
+        shape = tuple(int(v) for v in npz[prefix + "_shape"])
+        return sp.csc_matrix((npz[prefix + "_data"], npz[prefix + "_indices"], npz[prefix + "_indptr"]),
+                             shape=shape).tocsr()
+    return (npz["frames"], npz["mass"], mat("L"), npz["evals"][:k_eig], npz["evecs"][:, :k_eig],
+            mat("gradX"), mat("gradY"))

@@ -381,3 +381,113 @@ def test_net_training_step_and_gradient_allreduce(dn):
     opt.step()
     assert any(not torch.equal(a, b) for a, b in zip(before, [p_.detach() for p_ in net.parameters()]))
     assert float(min(b.diffusion.diffusion_time.min() for b in net.blocks)) >= 0.0
+
+
+# ---- data-side neighbours of the block ------------------------------------------------
+GEOM_CACHE = os.path.join(ROOT, "tests", "golden", "op_cache")
+
+
+def _csr_np(st):
+    _, rowptr, colidx, vals = st
+    return rowptr.cpu().numpy(), colidx.cpu().numpy(), vals.cpu().numpy()
+
+
+def test_operator_cache_to_device_matches_reference_hit_branch(dn):
+    """geometry.get_operators on the cache entry the reference wrote: every tensor of the tuple equals what the
+    reference's own cache-hit branch returned (bit-exact), and the CSR/CSR^T built straight from the file's CSC
+    arrays equal the ones the generic COO path builds."""
+    fx = load_golden("geom_small")
+    verts, faces = torch.from_numpy(fx["verts"]), torch.from_numpy(fx["faces"])
+    frames, mass, L, evals, evecs, gradX, gradY = dn.geometry.get_operators(verts, faces, 16, GEOM_CACHE,
+                                                                            device="cuda")
+    for got, key in ((frames, "frames"), (mass, "mass"), (evals, "evals"), (evecs, "evecs")):
+        assert got.is_cuda and got.dtype == torch.float32
+        assert np.array_equal(got.cpu().numpy(), fx[key]), key
+    for got, pre in ((L, "L"), (gradX, "gradX"), (gradY, "gradY")):
+        assert got.is_sparse and got.is_coalesced() and got.indices().dtype == torch.int64     # utils.py:55
+        assert np.array_equal(got.indices()[0].cpu().numpy(), fx[pre + "_rows"]), pre
+        assert np.array_equal(got.indices()[1].cpu().numpy(), fx[pre + "_cols"]), pre
+        assert np.array_equal(got.values().cpu().numpy(), fx[pre + "_vals"]), pre
+    pre_built = dn.ops.prepare_operators(gradX, gradY)
+    assert pre_built._coo is None            # the registered from_csc object, not a rebuild through COO
+    generic = dn.ops.GradOperators(gradX, gradY)
+    for a, b in zip(_csr_np(pre_built.csr), _csr_np(generic.csr)):
+        assert np.array_equal(a, b)
+    for a, b in zip(_csr_np(pre_built.csr_t), _csr_np(generic.csr_t)):
+        assert np.array_equal(a, b)
+    e12, v12 = dn.geometry.get_operators(verts, faces, 12, GEOM_CACHE, device="cuda")[3:5]
+    assert np.array_equal(e12.cpu().numpy(), fx["evals12"]) and np.array_equal(v12.cpu().numpy(), fx["evecs12"])
+    lists = dn.geometry.get_all_operators([verts, verts], [faces, faces], 16, GEOM_CACHE, device="cuda")
+    assert len(lists) == 7 and all(len(l) == 2 for l in lists)
+
+
+def test_hks_matches_reference(dn):
+    fx = load_golden("geom_small")
+    evals, evecs = dev(fx["evals"]), dev(fx["evecs"])
+    got = dn.geometry.compute_hks_autoscale(evals, evecs, 16)          # K=16: generic kernel
+    assert got.shape == (evecs.shape[0], 16)
+    assert O.rel_err(got.cpu().numpy(), fx["hks_f64"]) < 1e-5
+    got3 = dn.geometry.compute_hks(evals, evecs, dev(fx["hks3_scales"]))
+    assert O.rel_err(got3.cpu().numpy(), fx["hks3_f64"]) < 1e-5
+    gb = dn.geometry.compute_hks(torch.stack((evals, evals)), torch.stack((evecs, evecs)),
+                                 torch.stack((dev(fx["hks3_scales"]),) * 2))        # batched form, geometry.py:611-616
+    assert gb.shape == (2, evecs.shape[0], 3) and torch.equal(gb[0], got3) and torch.equal(gb[1], got3)
+
+
+@pytest.mark.parametrize("K,S", [(32, 16), (64, 16), (96, 5), (128, 16), (256, 16), (128, 17), (160, 16), (40, 1)])
+def test_hks_shapes_against_oracle(dn, K, S):
+    """warp-per-row register kernel (K in {32,64,96,128,256}, S<=16) and the generic one, vs the fp64 oracle."""
+    V = 3001
+    mass, L, evals, evecs, gX, gY = dn.synthetic.structural_operators(60, 50, K, seed=K + S, device="cuda")
+    evecs = evecs[:V].contiguous()
+    scales = torch.logspace(-2, 0.3, S, device="cuda")
+    got = dn.geometry.compute_hks(evals, evecs, scales).cpu().numpy()
+    want = O.compute_hks(evals.double().cpu().numpy(), evecs.double().cpu().numpy(), scales.double().cpu().numpy())
+    assert O.rel_err(got, want) < 2e-6
+
+
+def test_cache_to_hks_to_net_pipeline_matches_reference(dn):
+    """The experiments' data path end to end (human_segmentation_original.py:111-126): cache entry -> operators on
+    the device -> HKS input features -> DiffusionNet, against the reference's fp64 output."""
+    fx = load_golden("geom_small")
+    verts, faces = torch.from_numpy(fx["verts"]), torch.from_numpy(fx["faces"])
+    frames, mass, L, evals, evecs, gradX, gradY = dn.geometry.get_operators(verts, faces, 16, GEOM_CACHE,
+                                                                            device="cuda")
+    feats = dn.geometry.compute_hks_autoscale(evals, evecs, 16)
+    for eng in ENGINES:
+        dn.set_engine(eng)
+        net = dn.DiffusionNet(C_in=16, C_out=6, C_width=32, N_block=2, dropout=False)
+        net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in golden_params(fx).items()}, strict=True)
+        net = net.cuda().eval()
+        with torch.no_grad():
+            out = net(feats, mass, L=L, evals=evals, evecs=evecs, gradX=gradX, gradY=gradY)
+        assert O.rel_err(out.cpu().numpy(), fx["net_out_f64"]) < TOL[eng], eng
+    dn.set_engine("tc3x")
+
+
+def test_full_size_hks_and_transpose_properties(dn):
+    """V=200k (BASELINE size): (1) Phi^T M Phi = I  =>  sum_v mass[v] hks[v,s] = sum_k exp(-evals[k] t_s);
+    (2) transposing the CSR twice is the identity, bit for bit, and every row comes out column-sorted."""
+    mass, L, evals, evecs, gX, gY = dn.synthetic.structural_operators(400, 500, 128, seed=0, device="cuda")
+    V = mass.shape[0]
+    scales = torch.logspace(-2, 0, 16, device="cuda")
+    hks = dn.geometry.compute_hks(evals, evecs, scales)
+    lhs = (hks.double() * mass.double()[:, None]).sum(0)
+    rhs = torch.exp(-evals.double()[None, :] * scales.double()[:, None]).sum(1)
+    assert float(((lhs - rhs).abs() / rhs).max()) < 1e-4
+    g = dn.ops.prepare_operators(gX, gY)
+    st, rowptr, colidx, vals = g.csr
+    rp, ci, va = rowptr.cpu().numpy(), colidx.cpu().numpy(), vals.cpu().numpy()
+    t = dn.ops.GradOperators.from_csc(V, rp, ci, va[0::2], va[1::2], "cuda")      # treats csr as the CSC of A^T
+    # t.csr_t is the input verbatim; t.csr = its transpose = CSR of A^T
+    tt = dn.ops.GradOperators.from_csc(V, *[a.cpu().numpy() for a in t.csr[1:3]],
+                                       t.csr[3][0::2].cpu().numpy(), t.csr[3][1::2].cpu().numpy(), "cuda")
+    for a, b in zip(_csr_np(tt.csr), (rp, ci, va)):
+        assert np.array_equal(a, b)
+    trp, tci = t.csr[1].cpu().numpy(), t.csr[2].cpu().numpy()
+    assert trp[0] == 0 and trp[-1] == g.nnz
+    key = np.repeat(np.arange(V, dtype=np.int64), np.diff(trp)) * V + tci[:g.nnz]
+    assert np.all(np.diff(key) > 0)                       # rows ascending, columns strictly ascending inside a row
+    # and it matches the argsort-based transpose of the generic path
+    for a, b in zip(_csr_np(t.csr), _csr_np(g.csr_t)):
+        assert np.array_equal(a, b)

@@ -141,3 +141,40 @@ if r == 0: print("GLOO_OK")
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout + r.stderr
+
+
+# ---- operator cache, read side (geometry.py:426-519) -- host logic only ---------------------------------------
+def _geom():
+    import numpy as np
+    with np.load(os.path.join(GOLDEN, "geom_small.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_cache_probe_uses_the_reference_file_naming():
+    fx = _geom()
+    cache = os.path.join(GOLDEN, "op_cache")
+    verts, faces = torch.from_numpy(fx["verts"]), torch.from_numpy(fx["faces"])
+    assert dn.geometry.hash_arrays((fx["verts"], fx["faces"])) + "_0.npz" == str(fx["cache_file"])
+    npz = dn.geometry.find_cached_operators(verts, faces, 16, cache)
+    assert npz is not None and int(npz["k_eig"].item()) == 16
+    assert dn.geometry.find_cached_operators(verts, faces, 12, cache) is not None       # fewer eigenpairs: still a hit
+    assert dn.geometry.find_cached_operators(verts, faces, 17, cache) is None           # geometry.py:482-485
+    assert dn.geometry.find_cached_operators(verts + 1.0, faces, 16, cache) is None     # other mesh: miss
+
+
+def test_cache_miss_and_cpu_device_fail_loudly():
+    fx = _geom()
+    cache = os.path.join(GOLDEN, "op_cache")
+    verts, faces = torch.from_numpy(fx["verts"]), torch.from_numpy(fx["faces"])
+    with pytest.raises(NotImplementedError, match="populate the cache"):
+        dn.geometry.get_operators(verts + 1.0, faces, 16, cache, device="cuda")
+    with pytest.raises(NotImplementedError):
+        dn.geometry.get_operators(verts, faces, 16, None, device="cuda")
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        dn.geometry.get_operators(verts, faces, 16, cache)            # default device = verts.device = cpu
+    bad = verts.clone()
+    bad[0, 0] = float("nan")
+    with pytest.raises(RuntimeError, match="NaN verts"):              # geometry.py:438-439
+        dn.geometry.get_operators(bad, faces, 16, cache)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        dn.geometry.compute_hks(torch.zeros(4), torch.zeros(3, 4), torch.ones(2))

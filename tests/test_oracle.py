@@ -6,7 +6,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import load_golden, golden_params, ROOT
+from conftest import load_golden, golden_params, ROOT, GOLDEN
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import dn_oracle as O  # noqa: E402
@@ -99,3 +99,46 @@ def test_torch_port_matches_reference():
         out = T.block_forward(b(fx["x_in"]), b(base["mass"]), b(base["evals"]), b(base["evecs"]), [gX], [gY], p, **kw)
         assert O.rel_err(out[0].numpy(), fx["out_f32"]) < 1e-6
         assert O.rel_err(out[0].numpy(), fx["out_f64"]) < 2e-6
+
+
+# ---- data-side neighbours: pinned by oracle/make_golden_geom.py -----------------------
+def _cache_file():
+    d = os.path.join(GOLDEN, "op_cache")
+    files = sorted(os.listdir(d))
+    assert len(files) == 1
+    return os.path.join(d, files[0])
+
+
+def test_hks_matches_reference():
+    fx = load_golden("geom_small")
+    sc = O.hks_autoscale_scales(16)
+    got32 = O.compute_hks(fx["evals"], fx["evecs"], sc)
+    assert O.rel_err(got32, fx["hks_f32"]) < 2e-6
+    got64 = O.compute_hks(fx["evals"].astype(np.float64), fx["evecs"].astype(np.float64),
+                          np.logspace(-2.0, 0.0, num=16))
+    assert O.rel_err(got64, fx["hks_f64"]) < 1e-12
+    got3 = O.compute_hks(fx["evals"].astype(np.float64), fx["evecs"].astype(np.float64),
+                         fx["hks3_scales"].astype(np.float64))
+    assert O.rel_err(got3, fx["hks3_f64"]) < 1e-12
+
+
+def test_operator_cache_reader_matches_reference_hit_branch():
+    fx = load_golden("geom_small")
+    path = _cache_file()
+    assert os.path.basename(path) == str(fx["cache_file"])
+    assert os.path.basename(path) == O.cache_key(fx["verts"], fx["faces"]) + "_0.npz"
+    with np.load(path, allow_pickle=True) as npz:
+        frames, mass, L, evals, evecs, gX, gY = O.read_operator_cache(npz, 16)
+        e12, v12 = O.read_operator_cache(npz, 12)[3:5]
+    for got, key in ((frames, "frames"), (mass, "mass"), (evals, "evals"), (evecs, "evecs"),
+                     (e12, "evals12"), (v12, "evecs12")):
+        assert np.array_equal(got, fx[key]), key
+    V = mass.shape[0]
+    for got, pre in ((L, "L"), (gX, "gradX"), (gY, "gradY")):
+        want = O.coo_to_csr(fx[pre + "_rows"].astype(np.int64), fx[pre + "_cols"].astype(np.int64),
+                            fx[pre + "_vals"], (V, V))
+        got = got.copy()
+        got.sort_indices()
+        want.sort_indices()
+        assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices), pre
+        assert np.array_equal(got.data, want.data), pre
