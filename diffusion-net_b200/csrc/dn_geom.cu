@@ -29,35 +29,43 @@ __global__ void __launch_bounds__(256) hks_warp_kernel(const float* __restrict__
   }
   const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
   const int s_mine = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
-  for (int64_t row = warp; row < V; row += nwarps) {
-    const float* p = evecs + row * K + lane;
-    float phi2[KPL];
+  constexpr int RB = 4;                       // rows per warp iteration: 4 x K x 4 bytes of loads in flight per warp
+  for (int64_t row0 = warp * RB; row0 < V; row0 += nwarps * RB) {
+    float phi2[RB][KPL];
 #pragma unroll
-    for (int j = 0; j < KPL; ++j) {
-      const float f = __ldg(p + 32 * j);
-      phi2[j] = f * f;
+    for (int r = 0; r < RB; ++r) {
+      const bool ok = row0 + r < V;
+      const float* p = evecs + (row0 + r) * K + lane;
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        const float f = ok ? __ldg(p + 32 * j) : 0.f;
+        phi2[r][j] = f * f;
+      }
     }
-    float a[16];
 #pragma unroll
-    for (int s = 0; s < 16; ++s) {
-      float acc = 0.f;
+    for (int r = 0; r < RB; ++r) {
+      float a[16];
 #pragma unroll
-      for (int j = 0; j < KPL; ++j) acc = fmaf(coef[j][s], phi2[j], acc);
-      a[s] = acc;
+      for (int s = 0; s < 16; ++s) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) acc = fmaf(coef[j][s], phi2[r][j], acc);
+        a[s] = acc;
+      }
+      float b[8], c[4], d[2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        b[i] = (b4 ? a[i + 8] : a[i]) + __shfl_xor_sync(0xffffffffu, b4 ? a[i] : a[i + 8], 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        c[i] = (b3 ? b[i + 4] : b[i]) + __shfl_xor_sync(0xffffffffu, b3 ? b[i] : b[i + 4], 8);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        d[i] = (b2 ? c[i + 2] : c[i]) + __shfl_xor_sync(0xffffffffu, b2 ? c[i] : c[i + 2], 4);
+      float e = (b1 ? d[1] : d[0]) + __shfl_xor_sync(0xffffffffu, b1 ? d[0] : d[1], 2);
+      e += __shfl_xor_sync(0xffffffffu, e, 1);
+      if (!(lane & 1) && s_mine < S && row0 + r < V) out[(row0 + r) * S + s_mine] = e;
     }
-    float b[8], c[4], d[2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      b[i] = (b4 ? a[i + 8] : a[i]) + __shfl_xor_sync(0xffffffffu, b4 ? a[i] : a[i + 8], 16);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      c[i] = (b3 ? b[i + 4] : b[i]) + __shfl_xor_sync(0xffffffffu, b3 ? b[i] : b[i + 4], 8);
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-      d[i] = (b2 ? c[i + 2] : c[i]) + __shfl_xor_sync(0xffffffffu, b2 ? c[i] : c[i + 2], 4);
-    float e = (b1 ? d[1] : d[0]) + __shfl_xor_sync(0xffffffffu, b1 ? d[0] : d[1], 2);
-    e += __shfl_xor_sync(0xffffffffu, e, 1);
-    if (!(lane & 1) && s_mine < S) out[row * S + s_mine] = e;
   }
 }
 
@@ -154,8 +162,8 @@ int launch_compute_hks(const float* evals, const float* evecs, const float* scal
                        float* out, cudaStream_t st) {
   if (V <= 0 || S <= 0) return DN_OK;
   if (S <= 16 && K % 32 == 0 && K >= 32 && K <= 256 && (K / 32 <= 4 || K == 256)) {
-    int64_t blocks = (V * 32 + 255) / 256;
-    const int64_t cap = 148 * 8;          // grid-stride: the coefficient table is built once per warp
+    int64_t blocks = (V + 31) / 32;       // 8 warps x 4 rows per block iteration
+    const int64_t cap = 148 * 8;          // grid-stride: the coefficient table is built once per warp (4 rows/iteration)
     if (blocks > cap) blocks = cap;
     switch (K / 32) {
       case 1: hks_warp_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(evals, evecs, scales, V, S, out); break;
