@@ -45,8 +45,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+class dn_patches(C.Structure):
+    _fields_ = [("n_patches", C.c_int32), ("max_src", C.c_int32), ("tgt_ptr", C.c_void_p), ("tgt", C.c_void_p),
+                ("src_ptr", C.c_void_p), ("src_rows", C.c_void_p), ("ent_ptr", C.c_void_p), ("lcol", C.c_void_p),
+                ("vals", C.c_void_p)]
+
+
 class dn_csr(C.Structure):
-    _fields_ = [("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("vals", C.c_void_p), ("nnz", C.c_int64)]
+    _fields_ = [("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("vals", C.c_void_p), ("nnz", C.c_int64),
+                ("patches", C.POINTER(dn_patches))]
 
 
 class dn_block_params(C.Structure):
@@ -68,6 +75,7 @@ SIGNATURES = {
     "dn_kernel_launch_count": (_L, []),
     "dn_workspace_bytes": (_L, [_L, _I, _I]),
     "dn_csr_from_coo": (_I, [_P, _P, _P, _P, _L, _L, _P, _P, _P, _P]),
+    "dn_patch_build": (_L, [_L, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dn_csr_transpose": (_I, [C.POINTER(dn_csr), _L, _P, _P, _P, _P, _L, _P]),
     "dn_compute_hks": (_I, [_P, _P, _P, _L, _I, _I, _P, _P]),
     "dn_to_basis": (_I, [_P, _P, _P, _L, _I, _I, _P, _P, _L, _I, _P]),
@@ -103,7 +111,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.dn_abi_version() != 1:
+    if lib.dn_abi_version() != 2:
         raise RuntimeError("diffusion_net_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -1,6 +1,7 @@
 // C-ABI entry points (include/diffusion_net_b200.h).  Argument checking, workspace carving and
 // the kernel sequence of each reference function; no torch types, no hidden synchronisation.
 #include "dn_internal.h"
+#include <vector>
 #include <string.h>
 
 namespace {
@@ -126,6 +127,79 @@ int dn_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* vx, c
     return DN_ERR_INVALID_ARGUMENT;
   if (nnz >= (1ll << 31) || V >= (1ll << 31)) return DN_ERR_UNSUPPORTED;
   return launch_csr_from_coo(rows, cols, vx, vy, nnz, V, rowptr, colidx, vals, (cudaStream_t)stream);
+}
+
+int64_t dn_patch_build(int64_t V, const int32_t* rowptr, const int32_t* colidx, int max_targets, int max_src,
+                       int32_t* tgt_ptr, int32_t* tgt, int32_t* src_ptr, int32_t* src_rows, int32_t* ent_ptr,
+                       uint8_t* lcol, int32_t* perm, int32_t* max_src_out) {
+  if (V < 0 || !rowptr || max_targets < 1 || max_src < 1 || max_src > 256 || !tgt_ptr || !tgt || !src_ptr ||
+      !ent_ptr || !max_src_out || (V > 0 && rowptr[V] > 0 && (!colidx || !src_rows || !lcol || !perm)))
+    return DN_ERR_INVALID_ARGUMENT;
+  if (V >= (1ll << 31) - 1) return DN_ERR_UNSUPPORTED;
+  // state: 0 free, 1 queued by the patch being grown, 2 assigned
+  std::vector<int32_t> stamp((size_t)V, -1), lidx((size_t)V, 0), seeds, q;
+  std::vector<uint8_t> state((size_t)V, 0);
+  size_t seed_head = 0;
+  int64_t scan = 0, np = 0, nt = 0, nsr = 0, ne = 0;
+  int32_t worst = 0;
+  tgt_ptr[0] = 0; src_ptr[0] = 0; ent_ptr[0] = 0;
+  while (nt < V) {
+    int32_t s = -1;
+    while (seed_head < seeds.size()) {                       // prefer a vertex next to an earlier patch
+      const int32_t c = seeds[seed_head++];
+      if (state[c] == 0) { s = c; break; }
+    }
+    if (s < 0) {
+      while (state[scan] != 0) ++scan;
+      s = (int32_t)scan;
+    }
+    q.clear();
+    q.push_back(s);
+    state[s] = 1;
+    size_t qh = 0;
+    int nsrc = 0, ntg = 0;
+    while (qh < q.size() && ntg < max_targets) {
+      const int32_t v = q[qh++];
+      const int32_t rs = rowptr[v], re = rowptr[v + 1];
+      if (re - rs > max_src) return DN_ERR_UNSUPPORTED;
+      int newc = 0;
+      for (int32_t e = rs; e < re; ++e) newc += (stamp[colidx[e]] != (int32_t)np);
+      if (nsrc + newc > max_src) {                           // does not fit here: a later patch takes it
+        state[v] = 0;
+        seeds.push_back(v);
+        continue;
+      }
+      state[v] = 2;
+      tgt[nt++] = v;
+      ++ntg;
+      for (int32_t e = rs; e < re; ++e) {
+        const int32_t c = colidx[e];
+        if (stamp[c] != (int32_t)np) {
+          stamp[c] = (int32_t)np;
+          lidx[c] = nsrc++;
+          src_rows[nsr++] = c;
+        }
+        lcol[ne] = (uint8_t)lidx[c];
+        perm[ne] = e;
+        ++ne;
+      }
+      ent_ptr[nt] = (int32_t)ne;
+      for (int32_t e = rs; e < re; ++e) {
+        const int32_t c = colidx[e];
+        if (c < V && state[c] == 0) { state[c] = 1; q.push_back(c); }
+      }
+    }
+    for (; qh < q.size(); ++qh) {                            // frontier we did not get to: seeds of the next patches
+      const int32_t v = q[qh];
+      if (state[v] == 1) { state[v] = 0; seeds.push_back(v); }
+    }
+    if (nsrc > worst) worst = nsrc;
+    ++np;
+    tgt_ptr[np] = (int32_t)nt;
+    src_ptr[np] = (int32_t)nsr;
+  }
+  *max_src_out = worst;
+  return np;
 }
 
 int dn_csr_transpose(const dn_csr* in, int64_t V, int32_t* rowptr_out, int32_t* colidx_out, float* vals_out,

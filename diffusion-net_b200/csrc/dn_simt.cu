@@ -411,6 +411,118 @@ __global__ void __launch_bounds__(256) spmm_features_kernel(const int32_t* __res
   }
 }
 
+// Patch variant (dn_patches, built once for resident operators): one CTA per patch of graph-adjacent rows.
+// Phase 1 copies the patch's distinct neighbour rows of x_diffuse and [P|Q] into shared memory, coalesced, each row
+// exactly once; phase 2 is the same gather as above but out of shared memory.  At V = 200k the plain kernel moves
+// ~1.1 GB from L2 into the SMs (every neighbour row is re-fetched by ~half of the vertices that touch it: 47 % L1
+// hits); here it is (distinct rows / rows) x 1.5 KB per vertex.  Entries keep their CSR order and the arithmetic is
+// gather_row's, so the result is bit-identical.
+template <bool ROT>
+__global__ void __launch_bounds__(512) spmm_features_patch_kernel(const dn_patches P, const float* __restrict__ xd,
+                                                                  const float* __restrict__ pq, int ld_pq, int C,
+                                                                  float* __restrict__ feat) {
+  extern __shared__ float4 sm4[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int xq = C >> 2, pqq = ld_pq >> 2, rowf4 = xq + pqq;
+  const int p = blockIdx.x;
+  const int s0 = __ldg(P.src_ptr + p), ns = __ldg(P.src_ptr + p + 1) - s0;
+  const int t0 = __ldg(P.tgt_ptr + p), nt = __ldg(P.tgt_ptr + p + 1) - t0;
+  const float2* vals = reinterpret_cast<const float2*>(P.vals);
+
+  // per-row metadata of this warp's target, one entry per lane (coalesced), fetched one round ahead so that its
+  // latency hides behind the row copies (round 0) or the previous round's arithmetic
+  struct Meta { int64_t row; int es, n; int lc; float2 g; };
+  auto load_meta = [&](int i) {
+    Meta m;
+    m.row = 0; m.es = 0; m.n = 0; m.lc = 0; m.g = make_float2(0.f, 0.f);
+    if (i < nt) {
+      m.row = __ldg(P.tgt + t0 + i);
+      m.es = __ldg(P.ent_ptr + t0 + i);
+      m.n = __ldg(P.ent_ptr + t0 + i + 1) - m.es;
+      if (lane < m.n) { m.lc = __ldg(P.lcol + m.es + lane); m.g = __ldg(vals + m.es + lane); }
+    }
+    return m;
+  };
+  Meta cur = load_meta(warp);
+
+  // phase 1: distinct neighbour rows -> shared memory, four rows (12 x 16 B at C = 128) in flight per lane
+  for (int r = warp; r < ns; r += 4 * nwarps) {
+    int64_t row[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ok[u] = r + u * nwarps < ns;
+      row[u] = __ldg(P.src_rows + s0 + (ok[u] ? r + u * nwarps : r));
+    }
+    for (int c4 = lane; c4 < xq; c4 += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ldg4(xd + row[u] * C + 4 * c4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) sm4[(size_t)(r + u * nwarps) * rowf4 + c4] = v[u];
+    }
+    for (int c4 = lane; c4 < pqq; c4 += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ldg4(pq + row[u] * ld_pq + 4 * c4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) sm4[(size_t)(r + u * nwarps) * rowf4 + xq + c4] = v[u];
+    }
+  }
+  __syncthreads();
+
+  // phase 2: the gather, out of shared memory; entries in CSR order, gather_row's arithmetic
+  for (int i = warp; i < nt; i += nwarps) {
+    const Meta nxt = load_meta(i + nwarps);
+    for (int c4 = lane; c4 < xq; c4 += 32) {
+      Acc4 a;
+      a.gX = a.gY = a.bre = a.bim = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int base = 0; base < cur.n; base += 32) {
+        int lc_l = cur.lc;
+        float2 g_l = cur.g;
+        if (base > 0) {                                            // rows longer than a warp: next 32 entries
+          lc_l = 0; g_l = make_float2(0.f, 0.f);
+          if (base + lane < cur.n) { lc_l = __ldg(P.lcol + cur.es + base + lane); g_l = __ldg(vals + cur.es + base + lane); }
+        }
+        const int cnt = (cur.n - base) < 32 ? (cur.n - base) : 32;
+        for (int e = 0; e < cnt; ++e) {
+          const int lc = __shfl_sync(0xffffffffu, lc_l, e);
+          float2 g;
+          g.x = __shfl_sync(0xffffffffu, g_l.x, e);
+          g.y = __shfl_sync(0xffffffffu, g_l.y, e);
+          const float4* src = sm4 + (size_t)lc * rowf4;
+          const float4 x = src[c4];
+          const float4 Pv = src[xq + c4];
+          a.gX.x = fmaf(g.x, x.x, a.gX.x); a.gX.y = fmaf(g.x, x.y, a.gX.y);
+          a.gX.z = fmaf(g.x, x.z, a.gX.z); a.gX.w = fmaf(g.x, x.w, a.gX.w);
+          a.gY.x = fmaf(g.y, x.x, a.gY.x); a.gY.y = fmaf(g.y, x.y, a.gY.y);
+          a.gY.z = fmaf(g.y, x.z, a.gY.z); a.gY.w = fmaf(g.y, x.w, a.gY.w);
+          a.bre.x = fmaf(g.x, Pv.x, a.bre.x); a.bre.y = fmaf(g.x, Pv.y, a.bre.y);
+          a.bre.z = fmaf(g.x, Pv.z, a.bre.z); a.bre.w = fmaf(g.x, Pv.w, a.bre.w);
+          a.bim.x = fmaf(g.y, Pv.x, a.bim.x); a.bim.y = fmaf(g.y, Pv.y, a.bim.y);
+          a.bim.z = fmaf(g.y, Pv.z, a.bim.z); a.bim.w = fmaf(g.y, Pv.w, a.bim.w);
+          if (ROT) {
+            const float4 Q = src[2 * xq + c4];
+            a.bre.x = fmaf(-g.y, Q.x, a.bre.x); a.bre.y = fmaf(-g.y, Q.y, a.bre.y);
+            a.bre.z = fmaf(-g.y, Q.z, a.bre.z); a.bre.w = fmaf(-g.y, Q.w, a.bre.w);
+            a.bim.x = fmaf(g.x, Q.x, a.bim.x); a.bim.y = fmaf(g.x, Q.y, a.bim.y);
+            a.bim.z = fmaf(g.x, Q.z, a.bim.z); a.bim.w = fmaf(g.x, Q.w, a.bim.w);
+          }
+        }
+      }
+      float4 o;
+      o.x = tanhf(fmaf(a.gX.x, a.bre.x, a.gY.x * a.bim.x));
+      o.y = tanhf(fmaf(a.gX.y, a.bre.y, a.gY.y * a.bim.y));
+      o.z = tanhf(fmaf(a.gX.z, a.bre.z, a.gY.z * a.bim.z));
+      o.w = tanhf(fmaf(a.gX.w, a.bre.w, a.gY.w * a.bim.w));
+      *reinterpret_cast<float4*>(feat + cur.row * C + c4 * 4) = o;
+    }
+    cur = nxt;
+  }
+}
+
 // U[v] = [dd*Bre | dd*Bim | dd*gX | dd*gY],  dd = dfeat * (1 - feat^2)
 // Tuned variant for the common case (C/4) % 32 == 0 (one float4 per lane per 128 channels) and rows of <= 32
 // entries: the row's (col, gx, gy) triples are fetched once, coalesced, one per lane, and broadcast with
@@ -678,6 +790,30 @@ int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int 
                          float* feat, cudaStream_t st) {
   if (V <= 0) return DN_OK;
   if (C % 4) return DN_ERR_UNSUPPORTED;
+  static int use_patch = -1;
+  if (use_patch < 0) {
+    const char* e = getenv("DN_SPMM_PATCH");
+    use_patch = e ? atoi(e) : 1;
+  }
+  if (g->patches && use_patch && g->patches->n_patches > 0) {
+    const dn_patches& P = *g->patches;
+    const int ld = rotations ? 2 * C : C;
+    const size_t smem = (size_t)P.max_src * (size_t)(C + ld) * 4;
+    if (smem <= 227 * 1024) {
+      static size_t attr_set[2] = {0, 0};
+      if (smem > attr_set[rotations ? 1 : 0]) {
+        DN_CUDA_TRY(rotations ? cudaFuncSetAttribute(spmm_features_patch_kernel<true>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(spmm_features_patch_kernel<false>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[rotations ? 1 : 0] = smem;
+      }
+      if (rotations) spmm_features_patch_kernel<true><<<(unsigned)P.n_patches, 512, smem, st>>>(P, xd, pq, ld, C, feat);
+      else spmm_features_patch_kernel<false><<<(unsigned)P.n_patches, 512, smem, st>>>(P, xd, pq, ld, C, feat);
+      DN_LAUNCH_CHECK();
+      return DN_OK;
+    }
+  }
   const float2* vals = reinterpret_cast<const float2*>(g->vals);
   static int variant = -1;
   if (variant < 0) {

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 1
+#define DN_ABI_VERSION 2
 
 typedef void* dn_stream_t; /* cudaStream_t */
 
@@ -49,12 +49,32 @@ enum dn_engine { DN_ENGINE_SIMT = 0, DN_ENGINE_TC3X = 1, DN_ENGINE_TC1X = 2 };
 /* Shared-pattern CSR form of the (gradX, gradY) pair.  The reference hands over two
  * coalesced COO tensors with identical, row-sorted sparsity (Re/Im of one complex
  * matrix, geometry.py:381-382; utils.py:50-55).  vals holds (gx, gy) interleaved. */
+struct dn_patches;
 typedef struct dn_csr {
   const int32_t* rowptr; /* V+1 */
   const int32_t* colidx; /* nnz */
   const float* vals;     /* 2*nnz: gx0, gy0, gx1, gy1, ... */
   int64_t nnz;
+  const struct dn_patches* patches; /* optional (NULL): locality structure for the gather kernel, see below */
 } dn_csr;
+
+/* Optional locality structure over a dn_csr, built once per mesh (dn_patch_build, host side) for operators that
+ * stay resident.  The rows are grouped into patches of graph-adjacent vertices; the fused gradient-features
+ * kernel then stages the distinct neighbour rows of a patch in shared memory once (coalesced) and gathers from
+ * there, instead of re-fetching every neighbour row through L1/L2 for every vertex that touches it.  Results are
+ * bit-identical to the unpatched kernel (same entries, same order, same arithmetic).  The struct lives in host
+ * memory like dn_csr; the arrays are device arrays. */
+typedef struct dn_patches {
+  int32_t n_patches;
+  int32_t max_src;         /* largest number of distinct source rows of any patch (sizes the shared memory) */
+  const int32_t* tgt_ptr;  /* n_patches+1: the rows of patch p are tgt[tgt_ptr[p] .. tgt_ptr[p+1])           */
+  const int32_t* tgt;      /* V: row ids in patch order, every row exactly once                              */
+  const int32_t* src_ptr;  /* n_patches+1                                                                    */
+  const int32_t* src_rows; /* distinct column ids (= gathered rows) of each patch                            */
+  const int32_t* ent_ptr;  /* V+1: the entries of row tgt[i] are [ent_ptr[i], ent_ptr[i+1]) of lcol / vals   */
+  const uint8_t* lcol;     /* nnz: index into the patch's src_rows                                           */
+  const float* vals;       /* 2*nnz: (gx, gy) in patch order                                                 */
+} dn_patches;
 
 /* Parameters of one DiffusionNetBlock, named as in the reference state_dict
  * (layers.py:38, 110-113, 150-155).  nn.Linear layout: weight[n_out][n_in]. */
@@ -87,6 +107,16 @@ int64_t dn_workspace_bytes(int64_t V, int K, int C);
 int dn_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* vx, const float* vy,
                     int64_t nnz, int64_t V, int32_t* rowptr, int32_t* colidx, float* vals,
                     dn_stream_t stream);
+
+/* HOST-side operator prep (every pointer here is a HOST pointer): greedy breadth-first clustering of the CSR
+ * pattern into patches of at most max_targets rows whose distinct columns number at most max_src (<= 256).
+ * Outputs (caller-allocated): tgt_ptr, src_ptr (V+1 each: worst case one patch per row), tgt (V), src_rows (nnz),
+ * ent_ptr (V+1), lcol (nnz), perm (nnz: patch-order entry -> CSR entry, for permuting vals), max_src_out (1).
+ * Returns the number of patches, or a negative DN_ERR_* (a row longer than max_src is DN_ERR_UNSUPPORTED). */
+int64_t dn_patch_build(int64_t V, const int32_t* rowptr_host, const int32_t* colidx_host, int max_targets,
+                       int max_src, int32_t* tgt_ptr_host, int32_t* tgt_host, int32_t* src_ptr_host,
+                       int32_t* src_rows_host, int32_t* ent_ptr_host, uint8_t* lcol_host, int32_t* perm_host,
+                       int32_t* max_src_out_host);
 
 /* Operator prep from the reference's on-disk cache (geometry.py:548-568 stores gradX/gradY as scipy CSC; the
  * read side is geometry.py:494-519): a CSC matrix is the CSR of its transpose, so the cache arrays are `in`

@@ -491,3 +491,34 @@ def test_full_size_hks_and_transpose_properties(dn):
     # and it matches the argsort-based transpose of the generic path
     for a, b in zip(_csr_np(t.csr), _csr_np(g.csr_t)):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("permute", [False, True])
+@pytest.mark.parametrize("rot", [True, False])
+def test_patched_gather_is_bit_identical(dn, permute, rot):
+    """dn_patches (shared-memory staged gather) vs the plain gather kernel: same entries, same order, same arithmetic."""
+    dn.set_engine("tc3x")
+    C = 128
+    mass, L, evals, evecs, gX, gY = dn.synthetic.structural_operators(60, 70, 32, seed=2, device="cuda", permute=permute)
+    V = mass.shape[0]
+    g = torch.Generator().manual_seed(4)
+    xd = torch.randn(V, C, generator=g).cuda()
+    A_re = (torch.randn(C, C, generator=g) / C ** 0.5).cuda()
+    A_im = (torch.randn(C, C, generator=g) / C ** 0.5).cuda() if rot else None
+    plain = dn.ops.GradOperators(gX, gY)
+    with torch.no_grad():
+        ref = dn.ops.GradFeaturesFn.apply(xd, A_re, A_im, plain)
+        for T, R in ((64, 144), (32, 72), (7, 16)):
+            patched = dn.ops.GradOperators(gX, gY).build_patches(T, R)
+            assert patched._patches and patched.patch_stats["max_src"] <= R
+            out = dn.ops.GradFeaturesFn.apply(xd, A_re, A_im, patched)
+            assert torch.equal(out, ref), (T, R)
+    # second use of the same operator tensors: the structure is built only when the vertex order lacks locality
+    o1 = dn.ops.prepare_operators(gX, gY)
+    assert getattr(o1, "_patches", None) is None
+    o2 = dn.ops.prepare_operators(gX, gY)
+    assert o2 is o1
+    if dn.ops.auto_patch == "auto":
+        assert (o2.locality() < 0.05 and o2._patches) if permute else (o2.locality() > 0.3 and o2._patches is False)
+        with torch.no_grad():
+            assert torch.equal(dn.ops.GradFeaturesFn.apply(xd, A_re, A_im, o2), ref)

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_header_symbols():
     assert declared == set(dn._lib.SIGNATURES), declared ^ set(dn._lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dn_abi_version() == 1
+    assert lib.dn_abi_version() == 2
     assert lib.dn_error_string(-3).decode().startswith("diffusion_net_b200: workspace")
     assert lib.dn_workspace_bytes(200000, 128, 128) > 0
     assert lib.dn_workspace_bytes(-1, 128, 128) == -1
@@ -178,3 +178,54 @@ def test_cache_miss_and_cpu_device_fail_loudly():
         dn.geometry.get_operators(bad, faces, 16, cache)
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         dn.geometry.compute_hks(torch.zeros(4), torch.zeros(3, 4), torch.ones(2))
+
+
+# ---- dn_patch_build: host-side clustering for the gather kernel (include/diffusion_net_b200.h dn_patches) --------
+def _patch_build(rp, ci, V, T, R):
+    import ctypes as C
+    import numpy as np
+    nnz = len(ci)
+    tgt_ptr, src_ptr, ent_ptr = (np.empty(V + 1, np.int32) for _ in range(3))
+    tgt, src_rows, perm = np.empty(V, np.int32), np.empty(max(nnz, 1), np.int32), np.empty(max(nnz, 1), np.int32)
+    lcol, worst = np.empty(max(nnz, 1), np.uint8), np.zeros(1, np.int32)
+    hp = lambda a: C.c_void_p(a.ctypes.data)
+    n = dn._lib.load().dn_patch_build(V, hp(rp), hp(ci), T, R, hp(tgt_ptr), hp(tgt), hp(src_ptr), hp(src_rows),
+                                      hp(ent_ptr), hp(lcol), hp(perm), hp(worst))
+    return n, tgt_ptr, tgt, src_ptr, src_rows, ent_ptr, lcol, perm, int(worst[0])
+
+
+@pytest.mark.parametrize("permute", [False, True])
+def test_patch_build_covers_every_row_once_and_reproduces_the_spmm(permute):
+    import numpy as np
+    import scipy.sparse as sp
+    n_, m_ = 30, 41
+    V = n_ * m_
+    rows, cols = (np.asarray(a) for a in dn.synthetic.torus_pattern(n_, m_))
+    rng = np.random.default_rng(3)
+    A = sp.csr_matrix((rng.standard_normal(len(rows)).astype(np.float32), (rows, cols)), shape=(V, V))
+    A = sp.vstack([A[:17], sp.csr_matrix((3, V), dtype=np.float32), A[20:]]).tocsr()    # three empty rows
+    if permute:
+        pv = rng.permutation(V)
+        A = A[pv][:, pv].tocsr()
+    A.sort_indices()
+    rp, ci = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    for T, R in ((64, 144), (32, 72), (5, 9)):
+        n, tgt_ptr, tgt, src_ptr, src_rows, ent_ptr, lcol, perm, worst = _patch_build(rp, ci, V, T, R)
+        assert n > 0 and tgt_ptr[n] == V and ent_ptr[V] == A.nnz
+        assert np.array_equal(np.sort(tgt), np.arange(V))                      # every row exactly once
+        assert np.array_equal(np.sort(perm[:A.nnz]), np.arange(A.nnz))         # every entry exactly once
+        sizes, nsrc = np.diff(tgt_ptr[:n + 1]), np.diff(src_ptr[:n + 1])
+        assert sizes.min() >= 1 and sizes.max() <= T and nsrc.max() <= R and nsrc.max() == worst
+        # emulate the kernel: out[tgt[i]] = sum_e vals_p[e] * x[src_rows[src_ptr[p] + lcol[e]]], entries in CSR order
+        x = rng.standard_normal(V)
+        out = np.zeros(V)
+        vals_p = A.data[perm[:A.nnz]]
+        for p_ in range(n):
+            src = src_rows[src_ptr[p_]:src_ptr[p_ + 1]]
+            assert len(np.unique(src)) == len(src)
+            for i in range(tgt_ptr[p_], tgt_ptr[p_ + 1]):
+                e0, e1 = ent_ptr[i], ent_ptr[i + 1]
+                assert np.array_equal(perm[e0:e1], np.arange(rp[tgt[i]], rp[tgt[i] + 1]))   # row's entries, same order
+                out[tgt[i]] = np.dot(vals_p[e0:e1], x[src[lcol[e0:e1]]])
+        assert np.allclose(out, A @ x, rtol=1e-12, atol=1e-12)
+    assert _patch_build(rp, ci, V, 64, 3)[0] == -2                              # a row longer than max_src
