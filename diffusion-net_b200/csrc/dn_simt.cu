@@ -795,7 +795,9 @@ int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int 
     const char* e = getenv("DN_SPMM_PATCH");
     use_patch = e ? atoi(e) : 1;
   }
-  if (g->patches && use_patch && g->patches->n_patches > 0) {
+  // C == 128 only: that is the shape validated on the GPU (bit-identical to the plain kernel, both ROT variants); the
+  // phase-2 shuffles also assume every lane owns a float4 of the row (C/4 a multiple of 32)
+  if (g->patches && use_patch && g->patches->n_patches > 0 && C == 128) {
     const dn_patches& P = *g->patches;
     const int ld = rotations ? 2 * C : C;
     const size_t smem = (size_t)P.max_src * (size_t)(C + ld) * 4;

@@ -139,7 +139,7 @@ class GradOperators:
     def locality(self):
         """Share of entries whose column lies within 8 rows of their row: a proxy for how much of a row's gather the
         neighbouring warps of a CTA (8 consecutive rows) have already pulled into L1.  0.43 on a row-major grid
-        mesh, ~0 on a randomly permuted one.  (Index plumbing on the device.)"""
+        mesh, ~0.15 on a randomly permuted one (the diagonal stays).  (Index plumbing on the device.)"""
         if self.nnz == 0:
             return 1.0
         _, rowptr, colidx, _ = self.csr
@@ -222,6 +222,8 @@ PATCH_LOCALITY_THRESHOLD = 0.25
 
 def _maybe_patch(ops):
     if auto_patch == "0" or getattr(ops, "_patches", None) is not None:
+        return
+    if torch.cuda.is_current_stream_capturing():     # the decision needs host round trips: not inside a graph capture
         return
     if auto_patch == "1" or ops.locality() < PATCH_LOCALITY_THRESHOLD:
         ops.build_patches()

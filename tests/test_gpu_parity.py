@@ -519,6 +519,7 @@ def test_patched_gather_is_bit_identical(dn, permute, rot):
     o2 = dn.ops.prepare_operators(gX, gY)
     assert o2 is o1
     if dn.ops.auto_patch == "auto":
-        assert (o2.locality() < 0.05 and o2._patches) if permute else (o2.locality() > 0.3 and o2._patches is False)
+        # (a symmetric permutation keeps the diagonal entry on the diagonal: 1/7 of the entries stay 'local')
+        assert (o2.locality() < 0.2 and o2._patches) if permute else (o2.locality() > 0.3 and o2._patches is False)
         with torch.no_grad():
             assert torch.equal(dn.ops.GradFeaturesFn.apply(xd, A_re, A_im, o2), ref)
