@@ -6,6 +6,7 @@
 //   LearnedTimeDiffusion.forward layers.py:44-67, grad SpMM layers.py:216-223,
 //   SpatialGradientFeatures.forward layers.py:117-130, MiniMLP layers.py:133-164.
 #include "dn_internal.h"
+#include "dn_tc_ptx.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -523,6 +524,122 @@ __global__ void __launch_bounds__(512) spmm_features_patch_kernel(const dn_patch
   }
 }
 
+// Same patch gather with the copy and the gather overlapped: a persistent CTA (16 gather warps + 1 producer warp)
+// keeps TWO patches' rows in shared memory; the producer fetches them with bulk-async copies (cp.async.bulk, one per
+// row of x_diffuse and of [P|Q], mbarrier complete_tx), so no row passes through registers and the gather of patch k
+// runs while patch k+1 streams in.
+// STATUS: written at the end of round 1, compiled, NOT yet run on hardware -- opt-in only (DN_SPMM_PATCH_V=3);
+// the arithmetic and entry order are the validated kernel's.
+constexpr int PA_GATHER_WARPS = 16;
+constexpr int PA_THREADS = 32 * (PA_GATHER_WARPS + 1);
+
+template <bool ROT>
+__global__ void __launch_bounds__(PA_THREADS, 1)
+spmm_features_patch_async_kernel(const dn_patches P, const float* __restrict__ xd, const float* __restrict__ pq,
+                                 int ld_pq, int C, int buf_rows, float* __restrict__ feat) {
+  extern __shared__ __align__(128) uint8_t smraw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int xq = C >> 2, pqq = ld_pq >> 2, rowf4 = xq + pqq;
+  const uint32_t rowbytes = (uint32_t)rowf4 * 16u, bufbytes = (uint32_t)buf_rows * rowbytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + 2 * (size_t)bufbytes);
+  const uint32_t full = tc::smem_u32(bars), empty = tc::smem_u32(bars + 2);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(full + 8 * i, 1); tc::mbar_init(empty + 8 * i, PA_GATHER_WARPS); }
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  const float2* vals = reinterpret_cast<const float2*>(P.vals);
+  if (warp == PA_GATHER_WARPS) {
+    // ---- producer: rows of patch k -> buffer k & 1
+    uint32_t k = 0;
+    for (int p = blockIdx.x; p < P.n_patches; p += gridDim.x, ++k) {
+      const uint32_t b = k & 1, ph = (k >> 1) & 1;
+      const int s0 = __ldg(P.src_ptr + p), ns = __ldg(P.src_ptr + p + 1) - s0;
+      tc::mbar_wait(empty + 8 * b, ph ^ 1);
+      if (lane == 0) tc::mbar_arrive_expect_tx(full + 8 * b, (uint32_t)ns * rowbytes);
+      __syncwarp();
+      const uint32_t dst0 = tc::smem_u32(smraw) + b * bufbytes;
+      for (int r = lane; r < ns; r += 32) {
+        const int64_t row = __ldg(P.src_rows + s0 + r);
+        tc::tma_bulk_g2s(dst0 + (uint32_t)r * rowbytes, xd + row * C, (uint32_t)C * 4u, full + 8 * b);
+        tc::tma_bulk_g2s(dst0 + (uint32_t)r * rowbytes + (uint32_t)C * 4u, pq + row * ld_pq, (uint32_t)ld_pq * 4u,
+                         full + 8 * b);
+      }
+    }
+    return;
+  }
+  // ---- gather warps
+  struct Meta { int64_t row; int es, n; int lc; float2 g; };
+  uint32_t k = 0;
+  for (int p = blockIdx.x; p < P.n_patches; p += gridDim.x, ++k) {
+    const uint32_t b = k & 1, ph = (k >> 1) & 1;
+    const int t0 = __ldg(P.tgt_ptr + p), nt = __ldg(P.tgt_ptr + p + 1) - t0;
+    auto load_meta = [&](int i) {
+      Meta m;
+      m.row = 0; m.es = 0; m.n = 0; m.lc = 0; m.g = make_float2(0.f, 0.f);
+      if (i < nt) {
+        m.row = __ldg(P.tgt + t0 + i);
+        m.es = __ldg(P.ent_ptr + t0 + i);
+        m.n = __ldg(P.ent_ptr + t0 + i + 1) - m.es;
+        if (lane < m.n) { m.lc = __ldg(P.lcol + m.es + lane); m.g = __ldg(vals + m.es + lane); }
+      }
+      return m;
+    };
+    Meta cur = load_meta(warp);                                  // in flight while the rows land
+    tc::mbar_wait(full + 8 * b, ph);
+    const float4* sm4 = reinterpret_cast<const float4*>(smraw + (size_t)b * bufbytes);
+    for (int i = warp; i < nt; i += PA_GATHER_WARPS) {
+      const Meta nxt = load_meta(i + PA_GATHER_WARPS);
+      for (int c4 = lane; c4 < xq; c4 += 32) {                   // (C == 128: one iteration, every lane active)
+        Acc4 a;
+        a.gX = a.gY = a.bre = a.bim = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int base = 0; base < cur.n; base += 32) {
+          int lc_l = cur.lc;
+          float2 g_l = cur.g;
+          if (base > 0) {
+            lc_l = 0; g_l = make_float2(0.f, 0.f);
+            if (base + lane < cur.n) { lc_l = __ldg(P.lcol + cur.es + base + lane); g_l = __ldg(vals + cur.es + base + lane); }
+          }
+          const int cnt = (cur.n - base) < 32 ? (cur.n - base) : 32;
+          for (int e = 0; e < cnt; ++e) {
+            const int lc = __shfl_sync(0xffffffffu, lc_l, e);
+            float2 g;
+            g.x = __shfl_sync(0xffffffffu, g_l.x, e);
+            g.y = __shfl_sync(0xffffffffu, g_l.y, e);
+            const float4* src = sm4 + (size_t)lc * rowf4;
+            const float4 x = src[c4];
+            const float4 Pv = src[xq + c4];
+            a.gX.x = fmaf(g.x, x.x, a.gX.x); a.gX.y = fmaf(g.x, x.y, a.gX.y);
+            a.gX.z = fmaf(g.x, x.z, a.gX.z); a.gX.w = fmaf(g.x, x.w, a.gX.w);
+            a.gY.x = fmaf(g.y, x.x, a.gY.x); a.gY.y = fmaf(g.y, x.y, a.gY.y);
+            a.gY.z = fmaf(g.y, x.z, a.gY.z); a.gY.w = fmaf(g.y, x.w, a.gY.w);
+            a.bre.x = fmaf(g.x, Pv.x, a.bre.x); a.bre.y = fmaf(g.x, Pv.y, a.bre.y);
+            a.bre.z = fmaf(g.x, Pv.z, a.bre.z); a.bre.w = fmaf(g.x, Pv.w, a.bre.w);
+            a.bim.x = fmaf(g.y, Pv.x, a.bim.x); a.bim.y = fmaf(g.y, Pv.y, a.bim.y);
+            a.bim.z = fmaf(g.y, Pv.z, a.bim.z); a.bim.w = fmaf(g.y, Pv.w, a.bim.w);
+            if (ROT) {
+              const float4 Q = src[2 * xq + c4];
+              a.bre.x = fmaf(-g.y, Q.x, a.bre.x); a.bre.y = fmaf(-g.y, Q.y, a.bre.y);
+              a.bre.z = fmaf(-g.y, Q.z, a.bre.z); a.bre.w = fmaf(-g.y, Q.w, a.bre.w);
+              a.bim.x = fmaf(g.x, Q.x, a.bim.x); a.bim.y = fmaf(g.x, Q.y, a.bim.y);
+              a.bim.z = fmaf(g.x, Q.z, a.bim.z); a.bim.w = fmaf(g.x, Q.w, a.bim.w);
+            }
+          }
+        }
+        float4 o;
+        o.x = tanhf(fmaf(a.gX.x, a.bre.x, a.gY.x * a.bim.x));
+        o.y = tanhf(fmaf(a.gX.y, a.bre.y, a.gY.y * a.bim.y));
+        o.z = tanhf(fmaf(a.gX.z, a.bre.z, a.gY.z * a.bim.z));
+        o.w = tanhf(fmaf(a.gX.w, a.bre.w, a.gY.w * a.bim.w));
+        *reinterpret_cast<float4*>(feat + cur.row * C + c4 * 4) = o;
+      }
+      cur = nxt;
+    }
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(empty + 8 * b);               // this warp is done reading buffer b
+  }
+}
+
 // U[v] = [dd*Bre | dd*Bim | dd*gX | dd*gY],  dd = dfeat * (1 - feat^2)
 // Tuned variant for the common case (C/4) % 32 == 0 (one float4 per lane per 128 channels) and rows of <= 32
 // entries: the row's (col, gx, gy) triples are fetched once, coalesced, one per lane, and broadcast with
@@ -801,6 +918,31 @@ int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int 
     const dn_patches& P = *g->patches;
     const int ld = rotations ? 2 * C : C;
     const size_t smem = (size_t)P.max_src * (size_t)(C + ld) * 4;
+    static int patch_v = -1;
+    if (patch_v < 0) {
+      const char* e = getenv("DN_SPMM_PATCH_V");
+      patch_v = e ? atoi(e) : 2;
+    }
+    if (patch_v == 3 && 2 * smem + 64 <= 227 * 1024) {     // experimental: copy/gather overlapped (see the kernel)
+      const size_t smem3 = 2 * smem + 64;
+      static size_t attr3[2] = {0, 0};
+      if (smem3 > attr3[rotations ? 1 : 0]) {
+        DN_CUDA_TRY(rotations ? cudaFuncSetAttribute(spmm_features_patch_async_kernel<true>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)
+                              : cudaFuncSetAttribute(spmm_features_patch_async_kernel<false>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        attr3[rotations ? 1 : 0] = smem3;
+      }
+      int dev = 0, nsm = 148;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+      const unsigned grid = (unsigned)(P.n_patches < nsm ? P.n_patches : nsm);
+      if (rotations)
+        spmm_features_patch_async_kernel<true><<<grid, PA_THREADS, smem3, st>>>(P, xd, pq, ld, C, P.max_src, feat);
+      else
+        spmm_features_patch_async_kernel<false><<<grid, PA_THREADS, smem3, st>>>(P, xd, pq, ld, C, P.max_src, feat);
+      DN_LAUNCH_CHECK();
+      return DN_OK;
+    }
     if (smem <= 227 * 1024) {
       static size_t attr_set[2] = {0, 0};
       if (smem > attr_set[rotations ? 1 : 0]) {
