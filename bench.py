@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 N_TORUS, M_TORUS, K_EIG, C_WIDTH = 400, 500, 128, 128
 NNZ_ROW = 7
 METRIC = "DiffusionNetBlock forward Mverts/sec at V=200k,K=128,C=128; 1/2/4/8 GPU"
+WORKLOAD = "block_fwd V=200000 K=128 C=128, 1 mesh per GPU"      # identical in both arms (config.workload)
 
 
 def flops_per_vertex(K, C, r=NNZ_ROW):
@@ -109,31 +110,68 @@ def make_workload(dn, device, seed):
     return ops_t, params, x
 
 
-def cpu_port_step(T, host, params):
-    import torch
-    mass, L, evals, evecs, gradX, gradY, x = host
-    with torch.no_grad():
-        # stacked (B,V,V) sparse operators indexed per mesh, as DiffusionNet.forward hands them over
-        return T.block_forward(x.unsqueeze(0), mass.unsqueeze(0), evals.unsqueeze(0), evecs.unsqueeze(0),
-                               gradX.unsqueeze(0), gradY.unsqueeze(0), params)
-
-
-def time_cpu_port(host, params, steps, warmup):
-    """The reference's own CPU PyTorch path (oracle/dn_oracle_torch.py port) on all host threads."""
-    import torch
+def _reference_block(params, device):
+    """The reference's own DiffusionNetBlock (oracle/_ref, staged by oracle/stage_ref.py) with our seeded weights,
+    or None when no staged copy travelled to this box (then the torch restatement in oracle/ is timed instead)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import dn_oracle_torch as T   # the timed CPU arm; never on the product path
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    import ref_import                      # checker/baseline infrastructure; never on the product path
+    if not ref_import.reference_available():
+        return None
+    ref = ref_import.import_reference()
+    blk = ref.layers.DiffusionNetBlock(C_width=C_WIDTH, mlp_hidden_dims=[C_WIDTH, C_WIDTH], dropout=False)
+    blk.load_state_dict(params, strict=True)
+    return blk.to(device).eval()
+
+
+def make_baseline_step(host, params, device):
+    """One reference block forward (eval, fp32) on `device`: the reference module itself when staged (kind
+    "reference"), else its torch restatement (kind "port").  Stacked (B,V,V) sparse operators, as
+    DiffusionNet.forward hands them to the block."""
+    import torch
+    mass, L, evals, evecs, gradX, gradY, x = [t.to(device) for t in host]
+    xb, mb, eb, vb = x.unsqueeze(0), mass.unsqueeze(0), evals.unsqueeze(0), evecs.unsqueeze(0)
+    gxb, gyb = gradX.unsqueeze(0), gradY.unsqueeze(0)
+    blk = _reference_block(params, device)
+    if blk is not None:
+        def step():
+            with torch.no_grad():
+                return blk(xb, mb, None, eb, vb, gxb, gyb)
+        return step, "reference"
+    import dn_oracle_torch as T
+    prm = {k: v.to(device) for k, v in params.items()}
+
+    def step():
+        with torch.no_grad():
+            return T.block_forward(xb, mb, eb, vb, gxb, gyb, prm)
+    return step, "port"
+
+
+def time_cpu_baseline(host, params, steps, warmup):
+    """The reference's CPU PyTorch path on the host cores.  The thread count is picked by a small sweep (one step
+    each): oversubscribing the box (128 logical cores) was 3-4x slower than 8-32 threads in round 1."""
+    import torch
+    step, kind = make_baseline_step(host, params, "cpu")
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu} or {ncpu})
+    sweep = {}
+    step()                                           # first-touch / lazy init outside the sweep
+    for c in cands:
+        torch.set_num_threads(c)
+        step()
+        t0 = time.perf_counter()
+        step()
+        sweep[c] = time.perf_counter() - t0
+    best = min(sweep, key=sweep.get)
+    torch.set_num_threads(best)
     for _ in range(warmup):
-        cpu_port_step(T, host, params)
+        step()
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        cpu_port_step(T, host, params)
+        step()
         ts.append(time.perf_counter() - t0)
     ts.sort()
-    return ts[len(ts) // 2], cores
+    return ts[len(ts) // 2], best, kind, {str(k): round(v, 3) for k, v in sweep.items()}
 
 
 def run_reference(args, rank):
@@ -143,17 +181,52 @@ def run_reference(args, rank):
     V = N_TORUS * M_TORUS
     (mass, L, evals, evecs, gradX, gradY), params, x = make_workload(dn, "cpu", 0)
     steps, warm = max(1, args.steps), max(1, args.warmup)
-    sec, cores = time_cpu_port((mass, L, evals, evecs, gradX, gradY, x), params, steps, warm)
+    sec, cores, kind, sweep = time_cpu_baseline((mass, L, evals, evecs, gradX, gradY, x), params, steps, warm)
     val = V / sec / 1e6
-    sample = "full workload: 1 mesh V={} K={} C={}, {} steps (median), {} warm-up".format(V, K_EIG, C_WIDTH, steps, warm)
+    sample = "full workload: 1 mesh V={} K={} C={}, {} steps (median), {} warm-up; threads picked by sweep {}".format(
+        V, K_EIG, C_WIDTH, steps, warm, sweep)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mverts/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "block_fwd V=200000 K=128 C=128 (1 mesh, host CPU)", "device": "cpu"},
-        "cpu_baseline": {"value": val, "unit": "Mverts/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "device": "cpu (the reference's CPU PyTorch path on the host cores)"},
+        "cpu_baseline": {"value": val, "unit": "Mverts/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "Mverts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def measure_tf32_peak(dev, secs=1.0):
+    """cuBLAS TF32 GEMM (8192^3) on this GPU, burst (best of 10) and sustained (back to back for `secs`): the
+    denominator for kind::tf32 tensor-pipe fractions (MEASURED_PEAKS.json only holds the bf16 rate)."""
+    import torch
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize(dev)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        t0, cnt = time.time(), 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        while time.time() - t0 < secs:
+            for _ in range(10):
+                a @ b
+            cnt += 10
+            torch.cuda.synchronize(dev)
+        e1.record(); torch.cuda.synchronize(dev)
+        f = 2.0 * n ** 3 / 1e12
+        return {"tf32_tflops": f / (best * 1e-3), "tf32_tflops_sustained": f / (e0.elapsed_time(e1) / cnt * 1e-3),
+                "how": "torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS TF32), in this run"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 def main():
@@ -355,21 +428,47 @@ def main():
                              "tensor_pipe_frac is issued flops over that tf32 rate",
                      "block_hbm_frac": bytes_per_vertex(K_EIG, C) * V / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"]})
 
-    # ---- the reference's CPU path beside it (rank 0, N=1 only; bounded sample) ----
-    cpu = None
+    # ---- the reference beside it (rank 0, N=1 only; bounded samples) ----
+    cpu, gpu_base = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, cores = time_cpu_port((host_ops[0], host_ops[1], host_ops[2], host_ops[3], host_ops[4], host_ops[5],
-                                    x_host), params, 3, 1)
-        cpu = {"value": V / sec / 1e6, "unit": "Mverts/s", "cores": cores, "kind": "port",
-               "sample": "same workload (1 mesh V=200000), 3 steps median, 1 warm-up, torch-CPU port of the "
-                         "reference block forward"}
+        host = (host_ops[0], host_ops[1], host_ops[2], host_ops[3], host_ops[4], host_ops[5], x_host)
+        # (a) the same unmodified reference modules with CUDA tensors on THIS GPU: torch eager (cuBLAS fp32 with TF32
+        #     off, cuSPARSE) -- the "what a user gets today by calling .cuda()" bar
+        try:
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            gstep, gkind = make_baseline_step(host, params, dev)
+            for _ in range(3):
+                gstep()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                gstep()
+            b.record()
+            torch.cuda.synchronize()
+            gms = a.elapsed_time(b) / 10
+            torch.backends.cuda.matmul.allow_tf32 = prev
+            gpu_base = {"value": V / (gms * 1e-3) / 1e6, "unit": "Mverts/s", "ms_per_step": gms, "kind": gkind,
+                        "how": "reference DiffusionNetBlock, torch eager on this B200, fp32 (TF32 off), inputs resident, "
+                               "10 steps after 3 warm-up",
+                        "speedup_ours": gms / ms_step}
+            del gstep
+            torch.cuda.empty_cache()
+        except Exception as exc:                      # a baseline that cannot run must not take the bench line down
+            gpu_base = {"unavailable": repr(exc)[:200]}
+        # (b) the reference's CPU path on the host cores
+        sec, cores, kind, sweep = time_cpu_baseline(host, params, 3, 1)
+        cpu = {"value": V / sec / 1e6, "unit": "Mverts/s", "cores": cores, "kind": kind,
+               "sample": "same workload (1 mesh V=200000), 3 steps median, 1 warm-up; threads picked by a 1-step "
+                         "sweep (seconds per step): {}".format(sweep)}
 
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "Mverts/s", "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "block_fwd V=200000 K=128 C=128, 1 mesh per GPU", "engine": args.engine,
+            "config": {"workload": WORKLOAD, "engine": args.engine,
                        "parallelism": "mesh-sharded x{}".format(world), "l2": "inputs (~330 MB/step) exceed the 126 MB L2",
                        "gflop_per_step": flops_per_vertex(K_EIG, C_WIDTH) * V / 1e9,
                        "min_hbm_mb_per_step": bytes_per_vertex(K_EIG, C_WIDTH) * V / 1e6},
@@ -378,7 +477,7 @@ def main():
                     "steps": args.e2e_steps, "pipeline": "StreamedForward depth 2 (upload/compute/download streams)",
                     "operators_resident_value": e2e_resident,
                     "operators_resident_h2d_bytes_per_step": int(h["x"].numel() * 4)},
-            "roofline": roof, "stages_ms": stages, "cpu_baseline": cpu,
+            "roofline": roof, "stages_ms": stages, "cpu_baseline": cpu, "gpu_baseline": gpu_base,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -14,19 +14,22 @@ from . import ops
 
 
 def to_basis(values, basis, massvec):
-    """(B,V,D),(B,V,K),(B,V) -> (B,K,D): ``basis^T @ (values * massvec[...,None])`` (geometry.py:572-583)."""
+    """(B,V,D),(B,V,K),(B,V) -> (B,K,D): ``basis^T @ (values * massvec[...,None])`` (geometry.py:572-583).
+    Differentiable in ``values`` like the reference's ``torch.matmul`` version (backward = ``from_basis`` with the mass
+    as row scale); asking for gradients w.r.t. the operators raises."""
     if values.dim() == 2:
-        return ops.to_basis_raw(values, basis, massvec)
-    return torch.stack([ops.to_basis_raw(values[b], basis[b], massvec[b]) for b in range(values.shape[0])], 0)
+        return ops.to_basis(values, basis, massvec)
+    return torch.stack([ops.to_basis(values[b], basis[b], massvec[b]) for b in range(values.shape[0])], 0)
 
 
 def from_basis(values, basis):
-    """(B,K,D),(B,V,K) -> (B,V,D): ``basis @ values`` (geometry.py:586-598, real branch)."""
+    """(B,K,D),(B,V,K) -> (B,V,D): ``basis @ values`` (geometry.py:586-598, real branch).  Differentiable in ``values``
+    (backward = ``to_basis`` without mass)."""
     if values.is_complex() or basis.is_complex():
         raise NotImplementedError("complex from_basis is dead code in the reference (utils.cmatmul does not exist)")
     if values.dim() == 2:
-        return ops.from_basis_raw(values, basis)
-    return torch.stack([ops.from_basis_raw(values[b], basis[b]) for b in range(values.shape[0])], 0)
+        return ops.from_basis(values, basis)
+    return torch.stack([ops.from_basis(values[b], basis[b]) for b in range(values.shape[0])], 0)
 
 
 # ------------------------------------------------------------------------------------------------

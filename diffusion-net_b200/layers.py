@@ -70,7 +70,8 @@ class SpatialGradientFeatures(nn.Module):
         A_re, A_im = self.weights()
         lead = vectors.shape[:-3]
         v = vectors.reshape((-1,) + tuple(vectors.shape[-3:]))
-        needs_grad = torch.is_grad_enabled() and (vectors.requires_grad or A_re.requires_grad)
+        needs_grad = torch.is_grad_enabled() and (vectors.requires_grad or A_re.requires_grad or
+                                                  (A_im is not None and A_im.requires_grad))
         outs = []
         for b in range(v.shape[0]):
             if not needs_grad:

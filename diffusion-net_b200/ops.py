@@ -47,6 +47,12 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on(t):
+    """Context manager making ``t``'s device current for a C-ABI call: kernel attributes, the current stream and the
+    workspace are all per device (a model on cuda:1 while cuda:0 is current must launch on cuda:1)."""
+    return torch.cuda.device(t.device)
+
+
 _workspaces = {}
 _retired_workspaces = []
 pin_workspaces = False      # set by graphs.GraphedNet: never free a workspace a graph may point into
@@ -244,9 +250,18 @@ def _sweep_prep_cache():
         _prep_sweep_at = max(256, 2 * len(_prep_cache))
 
 
+def _evict_when_dead(key, *tensors):
+    """Drop a memoised entry (device CSR, transposed CSR, patches: ~17 MB per mesh at V = 200k) as soon as one of the
+    user's sparse tensors it was built from dies.  Training loops that re-upload the operators every step
+    (``gradX.to(device)``, as the reference's experiments do) would otherwise pile up dead entries."""
+    for t in tensors:
+        weakref.finalize(t, _prep_cache.pop, key, None)
+
+
 def prepare_operators(gradX, gradY):
     """Memoised on the identity (+ version) of the user's sparse tensors: the reference reuses the
-    same operator tensors across blocks and epochs (SURVEY.md section 8b 'Ownership')."""
+    same operator tensors across blocks and epochs (SURVEY.md section 8b 'Ownership').  Keep the operators
+    resident on the device: a fresh ``.to(device)`` copy every step is a cache miss (CSR rebuild + one host sync)."""
     key = (id(gradX), id(gradY))
     hit = _prep_cache.get(key)
     if hit is not None:
@@ -257,14 +272,16 @@ def prepare_operators(gradX, gradY):
     ops = GradOperators(gradX, gradY)
     _sweep_prep_cache()
     _prep_cache[key] = (weakref.ref(gradX), weakref.ref(gradY), (gradX._version, gradY._version), ops)
+    _evict_when_dead(key, gradX, gradY)
     return ops
 
 
 def register_prepared(gradX, gradY, ops):
     """Attach an already-built GradOperators to the sparse tensors a caller will pass to the layers
     (geometry.get_operators builds the CSR straight from the cache file)."""
-    _prep_cache[(id(gradX), id(gradY))] = (weakref.ref(gradX), weakref.ref(gradY),
-                                           (gradX._version, gradY._version), ops)
+    key = (id(gradX), id(gradY))
+    _prep_cache[key] = (weakref.ref(gradX), weakref.ref(gradY), (gradX._version, gradY._version), ops)
+    _evict_when_dead(key, gradX, gradY)
     _sweep_prep_cache()
 
 
@@ -279,7 +296,9 @@ def prepare_operators_batched(gradX, gradY):
                 _maybe_patch(o)
             return ops
     ops = [GradOperators(gradX[b], gradY[b]) for b in range(gradX.shape[0])]
+    _sweep_prep_cache()
     _prep_cache[key] = (weakref.ref(gradX), weakref.ref(gradY), (gradX._version, gradY._version), ops)
+    _evict_when_dead(key, gradX, gradY)
     return ops
 
 
@@ -292,23 +311,94 @@ def to_basis_raw(values, basis, massvec):
     V, K = basis.shape
     Cc = values.shape[-1]
     out = torch.empty(K, Cc, dtype=torch.float32, device=values.device)
-    ws = workspace(V, K, Cc, values.device)
-    _lib.check(_lib.load().dn_to_basis(values.data_ptr(), basis.data_ptr(),
-                                       _f32c(massvec).data_ptr() if massvec is not None else None, V, K, Cc,
-                                       out.data_ptr(), ws.data_ptr(), ws.numel(), _engine, _stream()), "dn_to_basis")
+    mv = _f32c(massvec) if massvec is not None else None
+    with _on(values):
+        ws = workspace(V, K, Cc, values.device)
+        _lib.check(_lib.load().dn_to_basis(values.data_ptr(), basis.data_ptr(),
+                                           mv.data_ptr() if mv is not None else None, V, K, Cc,
+                                           out.data_ptr(), ws.data_ptr(), ws.numel(), _engine, _stream()),
+                   "dn_to_basis")
     return out
 
 
-def from_basis_raw(values, basis):
-    _require_cuda(values, basis)
+def from_basis_raw(values, basis, row_scale=None):
+    _require_cuda(values, basis, row_scale)
     values, basis = _f32c(values), _f32c(basis)
     V, K = basis.shape
     Cc = values.shape[-1]
     out = torch.empty(V, Cc, dtype=torch.float32, device=values.device)
-    ws = workspace(V, K, Cc, values.device)
-    _lib.check(_lib.load().dn_from_basis(values.data_ptr(), basis.data_ptr(), None, V, K, Cc, out.data_ptr(),
-                                         ws.data_ptr(), ws.numel(), _engine, _stream()), "dn_from_basis")
+    rs = _f32c(row_scale) if row_scale is not None else None
+    with _on(values):
+        ws = workspace(V, K, Cc, values.device)
+        _lib.check(_lib.load().dn_from_basis(values.data_ptr(), basis.data_ptr(),
+                                             rs.data_ptr() if rs is not None else None, V, K, Cc, out.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _engine, _stream()), "dn_from_basis")
     return out
+
+
+def _device_guard(fn):
+    """Run an autograd Function's forward/backward with the device of its first tensor argument current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(ctx, *a):
+        t = next((x for x in a if torch.is_tensor(x)), None)
+        if t is None or not t.is_cuda:
+            return fn(ctx, *a)
+        with torch.cuda.device(t.device):
+            return fn(ctx, *a)
+    return wrapped
+
+
+def _no_operator_grads(*named):
+    for name, t in named:
+        if t is not None and t.requires_grad:
+            raise RuntimeError("diffusion_net_b200: gradients w.r.t. the operator tuple ({}) are not provided "
+                               "(the operators are data, SURVEY.md section 8a)".format(name))
+
+
+class ToBasisFn(torch.autograd.Function):
+    """geometry.py:572-583, differentiable in ``values``: d values = mass * (basis @ g)."""
+
+    @staticmethod
+    def forward(ctx, values, basis, massvec):
+        ctx.save_for_backward(basis, massvec)
+        return to_basis_raw(values, basis, massvec)
+
+    @staticmethod
+    def backward(ctx, g):
+        basis, massvec = ctx.saved_tensors
+        return from_basis_raw(_f32c(g), basis, row_scale=massvec), None, None
+
+
+class FromBasisFn(torch.autograd.Function):
+    """geometry.py:586-598 (real branch), differentiable in ``values``: d values = basis^T g."""
+
+    @staticmethod
+    def forward(ctx, values, basis):
+        ctx.save_for_backward(basis)
+        return from_basis_raw(values, basis)
+
+    @staticmethod
+    def backward(ctx, g):
+        (basis,) = ctx.saved_tensors
+        return to_basis_raw(_f32c(g), basis, None), None
+
+
+def to_basis(values, basis, massvec):
+    if torch.is_grad_enabled():
+        _no_operator_grads(("basis", basis), ("massvec", massvec))
+        if values.requires_grad:
+            return ToBasisFn.apply(values, basis, massvec)
+    return to_basis_raw(values, basis, massvec)
+
+
+def from_basis(values, basis):
+    if torch.is_grad_enabled():
+        _no_operator_grads(("basis", basis))
+        if values.requires_grad:
+            return FromBasisFn.apply(values, basis)
+    return from_basis_raw(values, basis)
 
 
 def compute_hks_raw(evals, evecs, scales):
@@ -329,8 +419,9 @@ def grad_spmm_raw(ops: GradOperators, x):
     x = _f32c(x)
     V, Cc = x.shape
     out = torch.empty(V, Cc, 2, dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().dn_grad_spmm(C.byref(ops.csr[0]), x.data_ptr(), V, Cc, out.data_ptr(), _stream()),
-               "dn_grad_spmm")
+    with _on(x):
+        _lib.check(_lib.load().dn_grad_spmm(C.byref(ops.csr[0]), x.data_ptr(), V, Cc, out.data_ptr(), _stream()),
+                   "dn_grad_spmm")
     return out
 
 
@@ -338,11 +429,14 @@ def spatial_gradient_features_raw(vectors, A_re, A_im):
     vectors = _f32c(vectors)
     V, Cc, _ = vectors.shape
     out = torch.empty(V, Cc, dtype=torch.float32, device=vectors.device)
-    ws = workspace(V, Cc, Cc, vectors.device)
-    _lib.check(_lib.load().dn_spatial_gradient_features_fwd(
-        vectors.data_ptr(), _f32c(A_re).data_ptr(), _f32c(A_im).data_ptr() if A_im is not None else None,
-        1 if A_im is not None else 0, V, Cc, out.data_ptr(), ws.data_ptr(), ws.numel(), _engine, _stream()),
-        "dn_spatial_gradient_features_fwd")
+    a_re = _f32c(A_re)                                  # contiguous copies stay referenced until the call returns
+    a_im = _f32c(A_im) if A_im is not None else None
+    with _on(vectors):
+        ws = workspace(V, Cc, Cc, vectors.device)
+        _lib.check(_lib.load().dn_spatial_gradient_features_fwd(
+            vectors.data_ptr(), a_re.data_ptr(), a_im.data_ptr() if a_im is not None else None,
+            1 if a_im is not None else 0, V, Cc, out.data_ptr(), ws.data_ptr(), ws.numel(), _engine, _stream()),
+            "dn_spatial_gradient_features_fwd")
     return out
 
 
@@ -353,19 +447,26 @@ def block_forward_raw(x_in, mass, evals, evecs, ops, time, A_re, A_im, weights, 
     V, Cc = x_in.shape
     K = evecs.shape[1]
     out = torch.empty_like(x_in)
-    ws = workspace(V, K, Cc, x_in.device)
     dims = [weights[0].shape[1]] + [w.shape[0] for w in weights]
-    wp = _lib.ptr_array([_f32c(w).data_ptr() for w in weights])
-    bp = _lib.ptr_array([_f32c(b).data_ptr() if b is not None else None for b in biases])
+    # contiguous copies (if any were needed) must outlive the launch: keep them in locals, not temporaries
+    wc = [_f32c(w) for w in weights]
+    bc = [_f32c(b) if b is not None else None for b in biases]
+    a_re = _f32c(A_re) if A_re is not None else None
+    a_im = _f32c(A_im) if A_im is not None else None
+    wp = _lib.ptr_array([w.data_ptr() for w in wc])
+    bp = _lib.ptr_array([b.data_ptr() if b is not None else None for b in bc])
     dm = _lib.int_array(dims)
     prm = _lib.dn_block_params(
-        time.data_ptr(), A_re.data_ptr() if A_re is not None else None,
-        A_im.data_ptr() if A_im is not None else None, 1 if with_features else 0,
-        1 if A_im is not None else 0, len(weights), wp, bp, dm)
+        time.data_ptr(), a_re.data_ptr() if a_re is not None else None,
+        a_im.data_ptr() if a_im is not None else None, 1 if with_features else 0,
+        1 if a_im is not None else 0, len(weights), wp, bp, dm)
     csr = C.byref(ops.csr[0]) if ops is not None else None
-    _lib.check(lib.dn_block_fwd(x_in.data_ptr(), mass.data_ptr(), evals.data_ptr(), evecs.data_ptr(), csr,
-                                C.byref(prm), V, K, Cc, out.data_ptr(), ws.data_ptr(), ws.numel(), _engine,
-                                _stream()), "dn_block_fwd")
+    with _on(x_in):
+        # the unfused MLP route carves 2 x V x max(hidden) floats: size the scratch by the widest layer
+        ws = workspace(V, K, max(Cc, max(dims[1:])), x_in.device)
+        _lib.check(lib.dn_block_fwd(x_in.data_ptr(), mass.data_ptr(), evals.data_ptr(), evecs.data_ptr(), csr,
+                                    C.byref(prm), V, K, Cc, out.data_ptr(), ws.data_ptr(), ws.numel(), _engine,
+                                    _stream()), "dn_block_fwd")
     return out
 
 
@@ -377,6 +478,7 @@ class DiffusionFn(torch.autograd.Function):
     """layers.py:44-67 spectral LearnedTimeDiffusion on one mesh."""
 
     @staticmethod
+    @_device_guard
     def forward(ctx, x, time, mass, evals, evecs):
         lib = _lib.load()
         x, mass, evals, evecs = _f32c(x), _f32c(mass), _f32c(evals), _f32c(evecs)
@@ -394,6 +496,7 @@ class DiffusionFn(torch.autograd.Function):
         return xd
 
     @staticmethod
+    @_device_guard
     def backward(ctx, g):
         lib = _lib.load()
         mass, evals, evecs, time, x_spec = ctx.saved_tensors
@@ -414,6 +517,7 @@ class GradFeaturesFn(torch.autograd.Function):
     """layers.py:216-226: sparse tangent gradient + SpatialGradientFeatures, fused."""
 
     @staticmethod
+    @_device_guard
     def forward(ctx, xd, A_re, A_im, ops):
         lib = _lib.load()
         xd, A_re = _f32c(xd), _f32c(A_re)
@@ -433,6 +537,7 @@ class GradFeaturesFn(torch.autograd.Function):
         return feat
 
     @staticmethod
+    @_device_guard
     def backward(ctx, g):
         lib = _lib.load()
         xd, pq, feat, A_re, A_im = ctx.saved_tensors
@@ -458,6 +563,7 @@ class MLPFn(torch.autograd.Function):
     (a bias slot may be None)."""
 
     @staticmethod
+    @_device_guard
     def forward(ctx, n_src, n_layers, has_res, drop_p, *t):
         lib = _lib.load()
         srcs = [_f32c(s) for s in t[:n_src]]
@@ -494,6 +600,7 @@ class MLPFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_device_guard
     def backward(ctx, g):
         lib = _lib.load()
         n_src, n_layers, has_res, dims, has_bias = ctx.meta

@@ -25,10 +25,21 @@ import numpy as np
 import scipy.sparse as sp
 
 REFERENCE_SRC = "/root/reference/src"
+# staged copy made by oracle/stage_ref.py (git-ignored, travels to the GPU box with the snapshot): lets
+# bench.py time the UNMODIFIED reference modules there, where /root/reference does not exist
+STAGED_SRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def reference_src():
+    """Directory holding the reference ``diffusion_net`` package: the mounted reference, else the staged copy."""
+    for d in (REFERENCE_SRC, STAGED_SRC):
+        if os.path.isfile(os.path.join(d, "diffusion_net", "layers.py")):
+            return d
+    return None
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_SRC, "diffusion_net"))
+    return reference_src() is not None
 
 
 def _cotan_laplacian(V, F, denom_eps=0.0):
@@ -64,8 +75,9 @@ def _vertex_areas(V, F):
 
 def import_reference():
     """Returns the reference ``diffusion_net`` package (layers, geometry, utils)."""
-    if not reference_available():
-        raise RuntimeError("reference not present at " + REFERENCE_SRC)
+    src = reference_src()
+    if src is None:
+        raise RuntimeError("reference not present at {} nor staged under {}".format(REFERENCE_SRC, STAGED_SRC))
     if "potpourri3d" not in sys.modules:
         pp3d = types.ModuleType("potpourri3d")
         pp3d.cotan_laplacian = _cotan_laplacian
@@ -73,8 +85,8 @@ def import_reference():
         sys.modules["potpourri3d"] = pp3d
     if "robust_laplacian" not in sys.modules:
         sys.modules["robust_laplacian"] = types.ModuleType("robust_laplacian")
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    if src not in sys.path:
+        sys.path.insert(0, src)
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
