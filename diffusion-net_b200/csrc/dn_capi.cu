@@ -495,9 +495,11 @@ int dn_mini_mlp_bwd(const float* grad_out, const float* const* src_host, const i
   return DN_OK;
 }
 
-int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const float* evecs, const dn_csr* grad,
-                 const dn_block_params* p, int64_t V, int K, int C, float* out, void* workspace, int64_t ws_bytes,
-                 int engine, dn_stream_t stream) {
+static int block_fwd_impl(const float* x_in, const float* mass, const float* evals, const float* evecs,
+                          const dn_csr* grad, const dn_block_params* p, int64_t V, int K, int C, float* out,
+                          void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream, cudaEvent_t* ev) {
+  // ev (optional, DN_PROFILE_STAGES + 1 events): recorded on the launching stream between the stages
+  auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], (cudaStream_t)stream); };
   if (!x_in || !mass || !evals || !evecs || !p || !p->diffusion_time || !out || V < 0 || K <= 0 || C <= 0)
     return DN_ERR_INVALID_ARGUMENT;
   if (p->with_gradient_features && (!grad || !grad->rowptr || !p->A_re || (p->with_gradient_rotations && !p->A_im)))
@@ -517,9 +519,12 @@ int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const
   float* partial = ws.take(pf);
   if (!S || !xd || !partial || (p->with_gradient_features && (!pq || !feat))) return DN_ERR_WORKSPACE;
   int rc, P = 0;
+  mark(0);
   // (a1) spectral diffusion: to_basis -> exp(-lambda t) -> from_basis   [layers.py:56-67]
   if ((rc = to_basis_partials(x_in, evecs, mass, V, K, C, partial, pf, &P, engine, st))) return rc;
+  mark(1);
   if ((rc = launch_spectral_scale(partial, P, evals, p->diffusion_time, K, C, nullptr, S, 1, st))) return rc;
+  mark(2);
 
   // every dense layer of the block: [0] from_basis, [1] (a5, commuted) [P|Q] = x_diffuse [A_re;A_im]^T,
   // [2..] cat -> MiniMLP -> + x_in  [layers.py:229-239]
@@ -566,6 +571,7 @@ int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const
     if (!pk) return DN_ERR_WORKSPACE;
     if ((rc = tc_pack_layers(first, cnt, pk, pb, st))) return rc;
   }
+  mark(3);
   float *t0 = nullptr, *t1 = nullptr;
   if (!tc_mlp && nm > 1) {
     t0 = ws.take(V * maxn);
@@ -582,10 +588,36 @@ int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const
     if (nfront == 2)
       if ((rc = run_chain(src_pq, &L[1], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
   }
+  mark(4);
   // (a4+a5) sparse tangent gradient + complex inner product + tanh   [layers.py:216-226,128-130]
   if (p->with_gradient_features)
     if ((rc = launch_spmm_features(grad, xd, pq, rot, V, C, feat, st))) return rc;
-  return run_chain(src_mlp, &L[nfront], nm, V, engine, t0, t1, tcws, tcws_bytes, st);
+  mark(5);
+  rc = run_chain(src_mlp, &L[nfront], nm, V, engine, t0, t1, tcws, tcws_bytes, st);
+  mark(6);
+  return rc;
+}
+
+int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const float* evecs, const dn_csr* grad,
+                 const dn_block_params* p, int64_t V, int K, int C, float* out, void* workspace, int64_t ws_bytes,
+                 int engine, dn_stream_t stream) {
+  return block_fwd_impl(x_in, mass, evals, evecs, grad, p, V, K, C, out, workspace, ws_bytes, engine, stream, nullptr);
+}
+
+int dn_block_fwd_profile(const float* x_in, const float* mass, const float* evals, const float* evecs,
+                         const dn_csr* grad, const dn_block_params* p, int64_t V, int K, int C, float* out,
+                         void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream, float* stage_ms_host) {
+  if (!stage_ms_host) return DN_ERR_INVALID_ARGUMENT;
+  cudaEvent_t ev[DN_PROFILE_STAGES + 1];
+  for (int i = 0; i <= DN_PROFILE_STAGES; ++i) DN_CUDA_TRY(cudaEventCreate(&ev[i]));
+  int rc = block_fwd_impl(x_in, mass, evals, evecs, grad, p, V, K, C, out, workspace, ws_bytes, engine, stream, ev);
+  if (rc == DN_OK) {
+    rc = (int)cudaEventSynchronize(ev[DN_PROFILE_STAGES]);
+    for (int i = 0; i < DN_PROFILE_STAGES && rc == DN_OK; ++i)
+      rc = (int)cudaEventElapsedTime(&stage_ms_host[i], ev[i], ev[i + 1]);
+  }
+  for (int i = 0; i <= DN_PROFILE_STAGES; ++i) cudaEventDestroy(ev[i]);
+  return rc;
 }
 
 }  // extern "C"

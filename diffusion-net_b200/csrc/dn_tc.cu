@@ -50,10 +50,7 @@ struct TcChainParams {
   TcLayer layer[DN_MAX_LAYERS];
   int n_layers;
   int passes;
-  int variant;
   int nmax;       // 128 or 256: widest layer (sizes the weight stages and the TMEM buffers)
-  int kch;        // K-chunk size the kernel instance uses (16 or 32)
-  int prefetch;   // sources are row-contiguous: bulk-prefetch the next tile into L2
   int64_t V;
   long long* trace;   // optional (tools/trace_chain.py): per-warp (event, clock64) pairs of CTA 0
   // TMEM plan of the TMEM-A kernel: accumulator column of buffer 0/1, number of buffers, first column and
@@ -183,17 +180,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
     // ===================== weight producer (bulk TMA; warp-uniform, one elected lane issues) =====
     uint32_t s = 0, ph = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t nt = tile + gridDim.x;
-      if (p.prefetch && (p.variant & 512) && nt < ntiles && elect_one()) {   // off by default: see below
-        // the next tile's 128 rows of every source are one contiguous block: pull them into L2 now.
-        // Measured (tools/ablate_mlp.py): this doubled the kernel's DRAM reads (564 vs 308 MB, ncu) and cost
-        // 10 % of its time, so it is disabled unless DN_TC_VARIANT has bit 512 set.
-        const int64_t r0 = nt * TILE_M;
-        const int64_t rows = (p.V - r0) < TILE_M ? (p.V - r0) : TILE_M;
-        for (int q = 0; q < p.src.nsrc; ++q)
-          l2_prefetch_bulk(p.src.ptr[q] + r0 * p.src.ld[q], (uint32_t)(rows * p.src.width[q] * 4));
-      }
-      __syncwarp();
       for (int l = 0; l < L; ++l) {
         const int N = p.layer[l].N, nch = p.layer[l].K / KC;
         const uint32_t img_bytes = (uint32_t)N * KC * 4;
@@ -204,12 +190,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
           mbar_wait(empty + 8 * s, ph ^ 1);
           DN_TRACE(31);
           if (elect_one()) {
-            if (p.variant & 32) {      // timing ablation only
-              mbar_arrive(full + 8 * s);
-            } else {
-              mbar_arrive_expect_tx(full + 8 * s, bytes);
-              tma_bulk_g2s(smem_u32(smB + s * b_stage), wsrc + (int64_t)c * 2 * N * KC, bytes, full + 8 * s);
-            }
+            mbar_arrive_expect_tx(full + 8 * s, bytes);
+            tma_bulk_g2s(smem_u32(smB + s * b_stage), wsrc + (int64_t)c * 2 * N * KC, bytes, full + 8 * s);
           }
           __syncwarp();
           if (++s == NS) { s = 0; ph ^= 1; }
@@ -220,7 +202,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
     // ===================== MMA issuer (warp-uniform loop; one elected lane issues) ==============
     // descriptor = template (LBO | SBO | version) + (smem address >> 4); k-steps / lo images are
     // constant increments of the address field
-    const uint64_t tmplA = (p.variant & 1) ? make_desc(0, 128, A_LBO) : make_desc(0, A_LBO, 128);
+    const uint64_t tmplA = make_desc(0, A_LBO, 128);
     const uint32_t smA_u = smem_u32(smA) >> 4, smB_u = smem_u32(smB) >> 4;
     uint32_t sa = 0, pa = 0, g = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
@@ -230,7 +212,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
         const uint32_t buf = (nbuf == 2) ? (g & 1) : 0, use = (nbuf == 2) ? (g >> 1) : g;
         const uint32_t d_tmem = tmem_base + buf * (uint32_t)nmax;
         const uint32_t b_lbo = (uint32_t)N * 16;
-        const uint64_t tmplB = (p.variant & 1) ? make_desc(0, 128, b_lbo) : make_desc(0, b_lbo, 128);
+        const uint64_t tmplB = make_desc(0, b_lbo, 128);
         const uint32_t b_img_u = ((uint32_t)N * KC * 4) >> 4, b_ks_u = (2 * b_lbo) >> 4;
         if (use > 0) {   // the epilogue of the previous user of this accumulator buffer must be done
           mbar_wait(d_empty + 8 * buf, (use - 1) & 1);
@@ -249,9 +231,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
               const uint64_t a_h = dah + ks * ((2 * A_LBO) >> 4), b_h = dbh + ks * b_ks_u;
               const uint32_t acc = (c | ks) ? 1u : 0u;
               if (p.passes == 3) {
-                if (!(p.variant & 8)) mma_tf32_ss(d_tmem, a_h + (A_IMG >> 4), b_h, idesc, acc);
-                if (!(p.variant & 8)) mma_tf32_ss(d_tmem, a_h, b_h + b_img_u, idesc, 1u);
-                if (!(p.variant & 8)) mma_tf32_ss(d_tmem, a_h, b_h, idesc, 1u);
+                mma_tf32_ss(d_tmem, a_h + (A_IMG >> 4), b_h, idesc, acc);
+                mma_tf32_ss(d_tmem, a_h, b_h + b_img_u, idesc, 1u);
+                mma_tf32_ss(d_tmem, a_h, b_h, idesc, 1u);
               } else {
                 mma_tf32_ss(d_tmem, a_h, b_h, idesc, acc);
               }
@@ -290,8 +272,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
       const int64_t st8 = 8 * p.src.ld[s];
 #pragma unroll
       for (int it = 0; it < 4; ++it)
-        r[it] = (8 * it < rem_rows && !(p.variant & 4)) ? __ldg(reinterpret_cast<const float4*>(base + it * st8))
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        r[it] = (8 * it < rem_rows) ? __ldg(reinterpret_cast<const float4*>(base + it * st8))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto store_chunk = [&](uint32_t cidx, const float4* r) {
       const uint32_t s = cidx % NS, ph = (cidx / NS) & 1;
@@ -301,9 +283,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
       uint8_t* a_hi = smA + s * A_STAGE + cv_off;
 #pragma unroll
       for (int it = 0; it < 4; ++it)
-        if (!(p.variant & 64)) store_split4(a_hi, a_hi + A_IMG, it * 128, r[it], p.passes);
+        store_split4(a_hi, a_hi + A_IMG, it * 128, r[it], p.passes);
       DN_TRACE(3);
-      if (!(p.variant & 2)) fence_proxy_async();
+      fence_proxy_async();
       __syncwarp();
       DN_TRACE(4);
       if (lane == 0) mbar_arrive(full + 8 * s);
@@ -337,7 +319,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
         const int rr_ = 32 * quarter + lane;
         const uint32_t ep_off = (rr_ >> 3) * 128 + (rr_ & 7) * 16;
         const int nco = Lr.N / KC;
-        const bool has_res = Lr.residual != nullptr && !(p.variant & 256);
+        const bool has_res = Lr.residual != nullptr;
         const uint32_t buf = (nbuf == 2) ? (g & 1) : 0, use = (nbuf == 2) ? (g >> 1) : g;
         auto load_res = [&](int c, float4* q) {
           const float4* rp = reinterpret_cast<const float4*>(Lr.residual + row * Lr.ld_res + c * KC);
@@ -354,14 +336,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
         const uint32_t d_lane = tmem_base + ((uint32_t)(32 * quarter) << 16) + buf * (uint32_t)nmax;
         for (int c = wg; c < nco; c += 2) {
           float v[16];
-          if (!(p.variant & 16)) tmem_ld16(d_lane + c * KC, v);
-          else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 1.f;
-          }
+          tmem_ld16(d_lane + c * KC, v);
           DN_TRACE(12);
           const int n0 = c * KC;
-          if (Lr.bias && !(p.variant & 256)) {
+          if (Lr.bias) {
             const float4* bp = bias_in_smem ? reinterpret_cast<const float4*>(sbias + l * 128 + n0)
                                             : reinterpret_cast<const float4*>(Lr.bias + n0);
 #pragma unroll
@@ -386,7 +364,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
             if (c + 2 < nco) load_res(c + 2, res);
           }
           DN_TRACE(13);
-          if (Lr.out && row < p.V && !(p.variant & 128)) {
+          if (Lr.out && row < p.V) {
             float4* op = reinterpret_cast<float4*>(Lr.out + row * Lr.ld_out + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -399,10 +377,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) rows_chain_kernel(const __gr
             uint8_t* a_hi = smA + s * A_STAGE + ep_off;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (!(p.variant & 64))
-                store_split4(a_hi, a_hi + A_IMG, j * A_LBO,
-                             make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), p.passes);
-            if (!(p.variant & 2)) fence_proxy_async();
+              store_split4(a_hi, a_hi + A_IMG, j * A_LBO,
+                           make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), p.passes);
+            fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(full + 8 * s);
             DN_TRACE(16);
@@ -793,408 +770,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rows_chain_ts_kernel(const __gr
 }
 
 // ---------------------------------------------------------------------------------------------
-// fused affine chain, TMA-fed, 32-wide K-stages  (every K % 128 == 0, every N % 32 == 0; N <= 128, or a
-// two-layer chain whose last layer has N = 256)
-//
-// Measured on the kernel above (tools/trace_chain.py style clock64 traces, profiles/r01_trace_*):
-//   * the single MMA warp spends ~800 cycles of its own time per 16-wide K-chunk -- barrier probes, elect,
-//     six UTCHMMA issues that block on the shallow tensor queue (~400 cycles = their execution time) and
-//     tcgen05.commit at ~150 cycles apiece -- so the tensor pipe cannot be more than ~50 % busy; removing the
-//     MMAs altogether shortens the kernel by only 10 %;
-//   * layer-0 operands are read with one row per lane (the TMEM lane = row mapping): every LDG.128 touches 32
-//     different cache lines, ~12k L1 wavefronts per 128-row tile, and the first chunk of a tile waits ~4-6k
-//     cycles behind that queue.  Two half-size CTAs per SM or two tiles in flight per CTA (both tried, both
-//     correct) were SLOWER (327 / 311 us vs 266 us for the MiniMLP at V = 200k): they add issue streams but
-//     also add load on exactly those two bottlenecks.
-// This kernel attacks both: (1) a pipeline stage is 32 k-columns -- twelve MMAs per barrier round trip and per
-// pair of commits instead of six; (2) layer-0 rows arrive by TMA: a dedicated warp issues 128x32 fp32 boxes
-// (SWIZZLE_128B tensor maps over the row-major sources) into a 4-deep shared-memory ring, and the converter
-// warps read their own row back with conflict-free LDS.128 (16-byte chunk j of row r sits at chunk j ^ (r & 7)),
-// split it into hi + lo and store it into the TMEM activation ring.  The first stage of the NEXT tile is
-// converted before the last epilogue of the current one, so the MMA warp runs from the last layer of one tile
-// straight into layer 0 of the next.
-// TMEM: N <= 128: two ping-pong accumulators [0,128) [128,256); 2-layer chain with N1 = 256: one accumulator
-// region [0,256) (layer 1 starts once every epilogue warp has pulled its layer-0 columns into registers);
-// [256,512): 4 stages of (hi32 | lo32).  Stage c of any layer is always produced by warpgroup c % 4 into ring
-// stage c % 4 (K % 128 == 0), so every stage has one in-order producer -- the mbarrier parity protocol needs that.
-// Warps: 0 weight TMA | 1 row-box TMA | 2 MMA | 3 idle | 4..19 four worker warpgroups.
-// ---------------------------------------------------------------------------------------------
-constexpr int T_THREADS = 640;
-constexpr int T_KS = 32;                      // k-columns per stage
-constexpr int T_RAW = TILE_M * T_KS * 4;      // 16 KiB: one 128 x 32 fp32 row box
-constexpr int T_NRAW = 4;
-constexpr int T_WST = 32768;                  // weight stage: the two packed 16-wide chunks (hi | lo) of one K-stage
-constexpr int T_NWS = 4;                      // == TMEM ring depth: stage s of both rings is released by ONE commit
-constexpr int T_WBYTES = T_NWS * T_WST;
-constexpr int T_SMEM = 1024 + T_NRAW * T_RAW + T_WBYTES + TS_BIAS_FLOATS * 4 + 512;
-
-struct TcTmaMaps {
-  CUtensorMap src[DN_MAX_SRC];   // 128-row x 32-column load boxes over the layer-0 sources
-  CUtensorMap res;               // same box shape over the last layer's residual matrix   (tail == 1 only)
-  CUtensorMap out;               // 32-row x 32-column store boxes over the last layer's output (tail == 1 only)
-  int tail;                      // 1: the last layer (N = 128, residual + output) reads its residual and writes
-};                               //    its output through TMA boxes staged in the row-box ring
-
-// shared memory -> global tensor box (bulk async group of the issuing thread)
-__device__ __forceinline__ void tma_box_s2g(const CUtensorMap* tmap, int col, int row, uint32_t src_smem) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                   reinterpret_cast<uint64_t>(tmap)),
-               "r"(col), "r"(row), "r"(src_smem)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit_wait_read() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
-__device__ __forceinline__ void tma_box_g2s(uint32_t dst_smem, const CUtensorMap* tmap, int col, int row, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(col), "r"(row), "r"(bar)
-      : "memory");
-}
-
-__global__ void __launch_bounds__(T_THREADS, 1)
-rows_chain_tma_kernel(const __grid_constant__ TcChainParams p, const __grid_constant__ TcTmaMaps maps) {
-  extern __shared__ uint8_t smem_raw_[];
-  const uint32_t smem0 = (smem_u32(smem_raw_) + 1023u) & ~1023u;          // SWIZZLE_128B boxes need 1024 B alignment
-  uint8_t* smem = smem_raw_ + (smem0 - smem_u32(smem_raw_));
-  const uint32_t raw_u = smem0;                                            // row boxes
-  uint8_t* smB = smem + T_NRAW * T_RAW;                                     // weight stages
-  float* sbias = reinterpret_cast<float*>(smB + T_WBYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + T_WBYTES + TS_BIAS_FLOATS * 4);
-  // bars: ra_full[4] ra_empty[4] a_full[4] a_empty[4] b_full[4] (unused[4]) d_full[2] d_empty[2]
-  // a_empty[s] releases BOTH the TMEM activation stage s and the weight stage s (the rings advance in lockstep):
-  // tcgen05.commit costs the MMA warp ~200 cycles, so one commit per stage instead of two.
-  const uint32_t ra_full = smem_u32(bars), ra_empty = smem_u32(bars + 4);
-  const uint32_t a_full = smem_u32(bars + 8), a_empty = smem_u32(bars + 12);
-  const uint32_t b_full = smem_u32(bars + 16);
-  const uint32_t d_full = smem_u32(bars + 24), d_empty = smem_u32(bars + 26);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int tr_n = 0;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(ra_full + 8 * i, 1); mbar_init(ra_empty + 8 * i, 4);
-      mbar_init(a_full + 8 * i, 4);  mbar_init(a_empty + 8 * i, 1);
-      mbar_init(b_full + 8 * i, 1);
-    }
-    for (int i = 0; i < 2; ++i) { mbar_init(d_full + 8 * i, 1); mbar_init(d_empty + 8 * i, 16); }
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<512>(smem_u32(tmem_slot));
-  for (int i = threadIdx.x; i < p.n_layers * 256; i += blockDim.x) {
-    const int l = i >> 8, n = i & 255;
-    sbias[i] = (p.layer[l].bias && n < p.layer[l].N) ? __ldg(p.layer[l].bias + n) : 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int L = p.n_layers;
-  const int64_t ntiles = (p.V + TILE_M - 1) / TILE_M;
-  const int nst0 = p.layer[0].K / T_KS;
-  const uint32_t nbuf = (uint32_t)p.nbuf;     // 2: ping-pong accumulators at 0 / 128; 1: one region at 0
-  constexpr uint32_t A_COL0 = 256;            // ring: 4 stages x (hi32 | lo32)
-
-  if (warp == 0) {
-    // ===================== weight producer: one bulk copy (two packed chunks) per stage =====================
-    uint32_t sb = 0, pb = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-      for (int l = 0; l < L; ++l) {
-        const int N = p.layer[l].N, nst = p.layer[l].K / T_KS;
-        const int64_t stage_floats = 2ll * (2ll * N * KC);
-        const uint32_t bytes = (uint32_t)(stage_floats * 4);
-        const float* wsrc = p.layer[l].wpack;
-        for (int c = 0; c < nst; ++c) {
-          mbar_wait(a_empty + 8 * sb, pb ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(b_full + 8 * sb, bytes);
-            tma_bulk_g2s(smem_u32(smB + sb * T_WST), wsrc + c * stage_floats, bytes, b_full + 8 * sb);
-          }
-          __syncwarp();
-          if (++sb == T_NWS) { sb = 0; pb ^= 1; }
-        }
-      }
-  } else if (warp == 1) {
-    // ===================== row-box producer: layer-0 operands, 128 rows x 32 columns per stage =====================
-    // Box order == the order every warpgroup consumes its ring slot in:
-    //   L0(t) stages [4 or 0 ..)  |  L0(t+1) stages 0..3 (converted before the last epilogue of t)  |  residual(t) 0..3
-    uint32_t sr = 0, pr = 0;
-    auto send = [&](const CUtensorMap* tm, int col, int64_t tile) {
-      mbar_wait(ra_empty + 8 * sr, pr ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(ra_full + 8 * sr, T_RAW);
-        tma_box_g2s(raw_u + sr * T_RAW, tm, col, (int)(tile * TILE_M), ra_full + 8 * sr);
-      }
-      __syncwarp();
-      if (++sr == T_NRAW) { sr = 0; pr ^= 1; }
-    };
-    auto send_l0 = [&](int c, int64_t tile) {
-      int k0 = c * T_KS, s = 0;
-      while (s + 1 < p.src.nsrc && k0 >= p.src.width[s]) { k0 -= p.src.width[s]; ++s; }
-      send(&maps.src[s], k0, tile);
-    };
-    bool early = false;                       // this tile's first four boxes went out with the previous tile
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t nt = tile + gridDim.x;
-      for (int c = early ? 4 : 0; c < nst0; ++c) send_l0(c, tile);
-      early = false;
-      if (maps.tail) {
-        if (nt < ntiles) {
-          for (int c = 0; c < 4; ++c) send_l0(c, nt);
-          early = true;
-        }
-        for (int c = 0; c < 4; ++c) send(&maps.res, c * T_KS, tile);
-      }
-    }
-  } else if (warp == 2) {
-    // ===================== MMA issuer: A from TMEM, B from shared memory =====================
-    const uint32_t smB_u = smem_u32(smB) >> 4;
-    uint32_t base = 0, g = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-      for (int l = 0; l < L; ++l, ++g) {
-        const int N = p.layer[l].N, nst = p.layer[l].K / T_KS;
-        const uint32_t idesc = make_idesc_tf32(TILE_M, N);
-        const uint32_t b_lbo = (uint32_t)N * 16;
-        const uint64_t tmplB = make_desc(0, b_lbo, 128);
-        const uint32_t b_img_u = ((uint32_t)N * KC * 4) >> 4, b_ks_u = (2 * b_lbo) >> 4;
-        const uint32_t b_chunk_u = 2 * b_img_u;
-        const uint32_t buf = (nbuf == 2) ? (g & 1) : 0, use = (nbuf == 2) ? (g >> 1) : g;
-        const uint32_t d_tmem = tmem_base + buf * 128u;
-        DN_TRACE(23);
-        if (use > 0) mbar_wait(d_empty + 8 * buf, (use - 1) & 1);
-        DN_TRACE(24);
-        uint32_t ready_a = mbar_test(a_full + 8 * (base & 3), (base >> 2) & 1);
-        uint32_t ready_b = mbar_test(b_full + 8 * (base & 3), (base >> 2) & 1);
-        for (int c = 0; c < nst; ++c) {
-          const uint32_t ii = base + (uint32_t)c, sa = ii & 3, pa = (ii >> 2) & 1, sb = sa;
-          DN_TRACE(20);
-          if (!ready_b) mbar_wait(b_full + 8 * sa, pa);
-          if (!ready_a) mbar_wait(a_full + 8 * sa, pa);
-          __syncwarp();
-          DN_TRACE(21);
-          tc_fence_after();
-          if (c + 1 < nst) {                                    // probe the next stage before issuing this one
-            ready_a = mbar_test(a_full + 8 * ((ii + 1) & 3), ((ii + 1) >> 2) & 1);
-            ready_b = mbar_test(b_full + 8 * ((ii + 1) & 3), ((ii + 1) >> 2) & 1);
-          }
-          if (elect_one()) {
-            const uint32_t a0 = tmem_base + A_COL0 + sa * 64u;
-            const uint64_t dbs = tmplB + (smB_u + sb * (T_WST >> 4));
-#pragma unroll
-            for (int ks = 0; ks < T_KS / 8; ++ks) {
-              const uint32_t a_hi = a0 + ks * 8, a_lo = a_hi + 32;
-              const uint64_t b_h = dbs + (uint32_t)(ks >> 1) * b_chunk_u + (uint32_t)(ks & 1) * b_ks_u;
-              const uint32_t acc = (c | ks) ? 1u : 0u;
-              if (p.variant & 4096) continue;                   // timing ablation: barrier traffic only
-              if (p.passes == 3) {
-                mma_tf32_ts(d_tmem, a_lo, b_h, idesc, acc);
-                mma_tf32_ts(d_tmem, a_hi, b_h + b_img_u, idesc, 1u);
-                mma_tf32_ts(d_tmem, a_hi, b_h, idesc, 1u);
-              } else {
-                mma_tf32_ts(d_tmem, a_hi, b_h, idesc, acc);
-              }
-            }
-            mma_commit(a_empty + 8 * sa);                       // releases TMEM stage sa and weight stage sa
-            if (c + 1 == nst) mma_commit(d_full + 8 * buf);
-          }
-          __syncwarp();
-          DN_TRACE(22);
-        }
-        base += (uint32_t)nst;
-      }
-  } else if (warp >= 4) {
-    // ===================== workers: four warpgroups (converter + epilogue) =====================
-    const int wg = (warp - 4) >> 2;           // owns stage c % 4 == wg of every layer
-    const int quarter = warp & 3;             // TMEM lane quarter: this lane owns tile row 32*quarter + lane
-    const int trow = 32 * quarter + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * quarter) << 16);
-    const uint32_t swz = (p.variant & 8192) ? 0u : (uint32_t)(trow & 7);
-
-    // hi/lo of 32 values -> TMEM ring stage (idx & 3), then hand the stage to the MMA warp
-    auto put_stage = [&](uint32_t idx, const float* x /*32*/) {
-      const uint32_t s = idx & 3, ph = (idx >> 2) & 1;
-      DN_TRACE(1);
-      mbar_wait(a_empty + 8 * s, ph ^ 1);
-      DN_TRACE(2);
-      tc_fence_after();
-      const uint32_t ta = lane_base + A_COL0 + s * 64;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) split_tf32_fast(x[16 * h + j], hi[j], lo[j]);
-        tmem_st16(ta + 16 * h, hi);
-        if (p.passes == 3) tmem_st16(ta + 32 + 16 * h, lo);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full + 8 * s);
-      DN_TRACE(5);
-    };
-
-    // layer-0 stage c (c % 4 == wg): row box in shared memory -> registers -> TMEM
-    uint32_t raw_use = 0;                     // how many boxes this warpgroup has consumed from raw stage `wg`
-    auto convert_stage = [&](uint32_t idx) {
-      DN_TRACE(30);
-      mbar_wait(ra_full + 8 * wg, raw_use & 1);
-      DN_TRACE(31);
-      const uint32_t rowaddr = raw_u + (uint32_t)wg * T_RAW + (uint32_t)trow * 128u;
-      float x[32];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t a = rowaddr + ((((uint32_t)j) ^ swz) << 4);
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(x[4 * j]), "=f"(x[4 * j + 1]), "=f"(x[4 * j + 2]), "=f"(x[4 * j + 3])
-                     : "r"(a));
-      }
-      // The release below must not overtake the loads above: LDS and mbarrier.arrive run in different pipes and the
-      // arrive has no register dependence on them, so without this the TMA refill could land under a load still in
-      // flight (seen on the GPU as a few rows of a tile computed from the NEXT box).  Reading one register of each
-      // 16-byte load makes the warp wait for all eight.
-      float landed = ((x[0] + x[4]) + (x[8] + x[12])) + ((x[16] + x[20]) + (x[24] + x[28]));
-      asm volatile("" ::"f"(landed) : "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ra_empty + 8 * wg);            // box is in registers: the TMA warp may refill it
-      ++raw_use;
-      put_stage(idx, x);
-    };
-
-    auto epilogue = [&](int l, int64_t tile, uint32_t g, uint32_t next_base) {
-      const TcLayer& Lr = p.layer[l];
-      const bool has_next = (l + 1 < L);
-      const int64_t row = tile * TILE_M + trow;
-      const bool rok = row < p.V;
-      const int nco = Lr.N / T_KS;
-      const bool has_res = Lr.residual != nullptr;
-      const uint32_t buf = (nbuf == 2) ? (g & 1) : 0, use = (nbuf == 2) ? (g >> 1) : g;
-      const float rs = (Lr.row_scale && rok) ? __ldg(Lr.row_scale + row) : 1.f;
-      const bool tail = maps.tail && !has_next;                  // residual in / output out through the row-box ring
-      float4 res[8];                                             // this warp's first residual stage: in flight
-      if (has_res && wg < nco && !tail) {                        // while the MMAs of the layer finish
-        const float4* rp = reinterpret_cast<const float4*>(Lr.residual + row * Lr.ld_res + wg * T_KS);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) res[j] = rok ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      DN_TRACE(10);
-      mbar_wait(d_full + 8 * buf, use & 1);
-      DN_TRACE(11);
-      tc_fence_after();
-      const uint32_t d_lane = lane_base + buf * 128u;
-      bool released = false;
-#pragma unroll 1
-      for (int c = wg; c < nco; c += 4) {
-        uint32_t q0[16], q1[16];
-        tmem_ld16_issue(d_lane + (uint32_t)c * T_KS, q0);
-        tmem_ld16_issue(d_lane + (uint32_t)c * T_KS + 16, q1);
-        tmem_ld_wait32(q0, q1);
-        if (c + 4 >= nco) {                                      // this warp's last accumulator read of the layer
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(d_empty + 8 * buf);
-          released = true;
-          DN_TRACE(12);
-        }
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(q0[j]); v[16 + j] = __uint_as_float(q1[j]); }
-        const int n0 = c * T_KS;
-        if (Lr.bias) {
-          const float4* bp = reinterpret_cast<const float4*>(sbias + l * 256 + n0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = bp[j];
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-          }
-        }
-        if (Lr.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (Lr.row_scale) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= rs;
-        }
-        if (tail) {
-          // residual box (this warpgroup's 32 columns) -> add -> the result overwrites this lane's own row of the box
-          // -> one TMA store per warp (32 rows x 32 columns; rows past V are clipped by the tensor map)
-          mbar_wait(ra_full + 8 * wg, raw_use & 1);
-          ++raw_use;
-          const uint32_t rowaddr = raw_u + (uint32_t)wg * T_RAW + (uint32_t)trow * 128u;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t a = rowaddr + ((((uint32_t)j) ^ swz) << 4);
-            float4 r;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
-            v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v[4 * j]), "f"(v[4 * j + 1]),
-                         "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                         : "memory");
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (elect_one()) {
-            tma_box_s2g(&maps.out, n0, (int)(tile * TILE_M) + 32 * quarter,
-                        raw_u + (uint32_t)wg * T_RAW + (uint32_t)quarter * 4096u);
-            tma_store_commit_wait_read();
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(ra_empty + 8 * wg);         // the slot may be refilled
-        } else if (has_res) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
-          }
-          if (c + 4 < nco) {
-            const float4* rp = reinterpret_cast<const float4*>(Lr.residual + row * Lr.ld_res + n0 + 4 * T_KS);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) res[j] = rok ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        if (Lr.out && rok && !tail) {
-          float4* op = reinterpret_cast<float4*>(Lr.out + row * Lr.ld_out + n0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        if (has_next) put_stage(next_base + (uint32_t)c, v);
-      }
-      if (!released) {                                           // narrow layer: nothing to read, still release
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(d_empty + 8 * buf);
-      }
-      DN_TRACE(14);
-    };
-
-    uint32_t idx = 0, g = 0;                  // idx: ring-stage index of the next layer's stage 0
-    bool pre = false;                         // this tile's first layer-0 stage is already converted
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t nt = tile + gridDim.x;
-      for (int c = pre ? wg + 4 : wg; c < nst0; c += 4) convert_stage(idx + (uint32_t)c);
-      idx += (uint32_t)nst0;
-      pre = false;
-      for (int l = 0; l < L; ++l, ++g) {
-        const bool last = (l + 1 == L);
-        if (last && nt < ntiles && wg < nst0) {                  // MMA can run on into the next tile under our epilogue
-          convert_stage(idx + (uint32_t)wg);
-          pre = true;
-        }
-        epilogue(l, tile, g, idx);
-        if (!last) idx += (uint32_t)(p.layer[l].N / T_KS);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 0) tmem_dealloc<512>(tmem_base);
-}
-
-// ---------------------------------------------------------------------------------------------
 // to_basis, split over V:  partial[cta][k][c] = sum_{v in cta's range} Phi[v][k] * m[v] * x[v][c]
 //   A = Phi^T (M = K_eig rows, padded to 128), B = (m x)^T (N = C rows); reduction dim = v.
 //   Both operands are transposed on the fly: each lane loads a 4(v) x 4(k) block with float4
@@ -1218,7 +793,7 @@ struct TcToBasisParams {
   const float* mass;     // (V) or null
   float* partial;        // (grid, K, C)
   int64_t V;
-  int K, C, passes, variant;
+  int K, C, passes;
   int64_t chunks_per_cta;
 };
 
@@ -1275,8 +850,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
   } else if (warp == 1) {
     // ===== MMA issuer (warp-uniform loop; one elected lane issues) =====
     const uint32_t idesc = make_idesc_tf32(128, p.C);
-    uint32_t lbo = TB_LBO, sbo = TB_SBO;
-    if (p.variant & 1) { lbo = TB_SBO; sbo = TB_LBO; }
+    const uint32_t lbo = TB_LBO, sbo = TB_SBO;
     for (int64_t c = 0; c < nch; ++c) {
       const uint32_t s = c % TB_NOP, ph = (c / TB_NOP) & 1;
       mbar_wait(op_full + 8 * s, ph);
@@ -1403,81 +977,71 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
   if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
-int g_tc_ok = -1;
 long long* g_trace_ptr = nullptr;
-int g_sm_count = 0;
 
-int env_variant() {
-  const char* e = getenv("DN_TC_VARIANT");
-  return e ? atoi(e) : 0;
-}
+// Per-device state: capability, SM count, and whether the >48 KB dynamic shared memory attributes were set on that
+// device (function attributes are per device: a process that drives several GPUs needs them on each one).
+constexpr int kMaxDev = 64;
+struct DevState { int tried, ok, sms; };
+DevState g_dev[kMaxDev];
 
 }  // namespace
 
-extern "C" void dn_debug_set_trace(void* device_buffer) { g_trace_ptr = static_cast<long long*>(device_buffer); }
+static int g_trace_skip = 0;   // chain launches to let pass before the traced one
+extern "C" void dn_debug_set_trace(void* device_buffer) { g_trace_ptr = static_cast<long long*>(device_buffer); g_trace_skip = 0; }
+// trace the k-th (0-based) chain-kernel launch after this call instead of every launch
+extern "C" void dn_debug_set_trace_launch(int k) { g_trace_skip = k; }
+static long long* take_trace_ptr() {
+  if (!g_trace_ptr) return nullptr;
+  if (g_trace_skip > 0) { --g_trace_skip; return nullptr; }
+  if (g_trace_skip == 0) { g_trace_skip = -1; return g_trace_ptr; }
+  return nullptr;   // already used once
+}
 
-bool tc_supported_device() {
-  if (g_tc_ok < 0) {
-    int dev = 0;
+// declared in dn_chain.cu
+int tc_chain3_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers);
+int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, int64_t V, int passes, int sm_count,
+                   long long* trace, cudaStream_t st);
+
+static DevState* cur_dev_state() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  DevState& d = g_dev[dev];
+  if (!d.tried) {
+    d.tried = 1;
     cudaDeviceProp prop;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
-      g_tc_ok = 0;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+      cudaGetLastError();
+      d.ok = 0;
     } else {
-      g_tc_ok = (prop.major == 10) ? 1 : 0;
-      g_sm_count = prop.multiProcessorCount;
-      if (g_tc_ok) {
+      d.ok = (prop.major == 10) ? 1 : 0;
+      d.sms = prop.multiProcessorCount;
+      if (d.ok) {
         if (cudaFuncSetAttribute(rows_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM) !=
                 cudaSuccess ||
             cudaFuncSetAttribute(rows_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
             cudaFuncSetAttribute(rows_chain_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM) !=
                 cudaSuccess ||
-            cudaFuncSetAttribute(rows_chain_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) !=
-                cudaSuccess ||
             cudaFuncSetAttribute(to_basis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM) !=
                 cudaSuccess) {
           cudaGetLastError();
-          g_tc_ok = 0;
+          d.ok = 0;
         }
       }
     }
     const char* off = getenv("DN_TC_DISABLE");
-    if (off && atoi(off)) g_tc_ok = 0;
+    if (off && atoi(off)) d.ok = 0;
   }
-  return g_tc_ok == 1;
+  return &d;
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
-typedef CUresult (*TmaEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static TmaEncodeFn tma_encode_fn() {
-  static TmaEncodeFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<TmaEncodeFn>(f);
-    else
-      cudaGetLastError();
-  }
-  return fn;
-}
-
-// rows x width fp32 matrix (leading dimension ld) -> tensor map of box_rows x 32-column boxes, SWIZZLE_128B;
-// rows past V read as zeros and are not written
-static int make_row_box_map(CUtensorMap* m, const float* ptr, int width, int64_t ld, int64_t V, int box_rows) {
-  const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)V};
-  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)T_KS, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = tma_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
-                                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : 1;
+bool tc_supported_device() {
+  DevState* d = cur_dev_state();
+  return d && d->ok == 1;
 }
 
 static bool ts_allowed_env() {
@@ -1485,7 +1049,8 @@ static bool ts_allowed_env() {
   return !e || atoi(e) != 0;
 }
 
-int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers) {
+// shapes the round-1 kernels (rows_chain_kernel / rows_chain_ts_kernel) take
+static int tc_rows_chain_legacy_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers) {
   if (n_layers < 1 || n_layers > DN_MAX_LAYERS) return DN_ERR_UNSUPPORTED;
   int k0 = 0;
   for (int s = 0; s < src.nsrc; ++s) {
@@ -1510,6 +1075,11 @@ int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_l
   }
   if (!layers[n_layers - 1].out) return DN_ERR_UNSUPPORTED;
   return DN_OK;
+}
+
+int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers) {
+  if (tc_chain3_supported(src, layers, n_layers) == DN_OK) return DN_OK;
+  return tc_rows_chain_legacy_supported(src, layers, n_layers);
 }
 
 int64_t tc_chain_ws_bytes(const DnLayer* layers, int n_layers) {
@@ -1545,7 +1115,8 @@ int tc_pack_layers(DnLayer* layers, int n_layers, void* ws, int64_t ws_bytes, cu
 int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers_in, int n_layers, int64_t V, int passes, void* ws,
                   int64_t ws_bytes, cudaStream_t st) {
   if (V <= 0) return DN_OK;
-  if (!tc_supported_device()) return DN_ERR_NOT_SM100;
+  DevState* dv = cur_dev_state();
+  if (!dv || dv->ok != 1) return DN_ERR_NOT_SM100;
   DnLayer layers[DN_MAX_LAYERS];
   bool packed = true;
   for (int l = 0; l < n_layers; ++l) {
@@ -1556,21 +1127,22 @@ int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers_in, int n_layers, 
     int rc = tc_pack_layers(layers, n_layers, ws, ws_bytes, st);
     if (rc) return rc;
   }
+  // default: the TMA-fed kernel of dn_chain.cu; shapes outside its envelope run the round-1 kernels below
+  if (tc_chain3_supported(src, layers, n_layers) == DN_OK) {
+    const int rc = tc_rows_chain3(src, layers, n_layers, V, passes, dv->sms, take_trace_ptr(), st);
+    if (rc != DN_ERR_UNSUPPORTED) return rc;
+  }
+  if (tc_rows_chain_legacy_supported(src, layers, n_layers) != DN_OK) return DN_ERR_UNSUPPORTED;
   TcChainParams p;
   memset(&p, 0, sizeof(p));
   p.src = src;
   p.n_layers = n_layers;
   p.passes = passes;
-  p.variant = env_variant();
   p.V = V;
   p.trace = g_trace_ptr;
   p.nmax = 128;
-  p.prefetch = 1;
-  p.kch = KC;
   for (int l = 0; l < n_layers; ++l)
     if (layers[l].N > 128) p.nmax = 256;
-  for (int s = 0; s < src.nsrc; ++s)
-    if (src.ld[s] != src.width[s]) p.prefetch = 0;
   // TMEM plan of the TMEM-A kernel
   p.acc_col[0] = 0; p.acc_col[1] = 128; p.nbuf = 2; p.a_col0 = 256; p.nsa = 8;
   if (p.nmax == 256 && n_layers == 1) { p.acc_col[1] = 0; p.nbuf = 1; }
@@ -1597,56 +1169,13 @@ int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers_in, int n_layers, 
     const char* e = getenv("DN_TC_TS");
     use_ts = e ? atoi(e) : 2;   // 0: never, 1: always, 2 (default): for chained layers
   }
-  // measured on B200 (V=200k): MiniMLP chain 301 us (TMEM-A) vs 347 us (smem operands); single layers are a few
-  // microseconds faster with two co-resident smem-operand CTAs per SM
-  // TMA-fed kernel with 32-wide stages (rows_chain_tma_kernel): K % 128 == 0, N % 32 == 0, row-box tensor maps.
-  // EXPERIMENTAL, opt-in (DN_TC_TMA=1): measured on B200 at V = 200k the MiniMLP chain runs in 258 us (vs 265 us for
-  // the kernel above) and in 239 us with the TMA residual-in / output-out tail (DN_TC_TMA_TAIL=1), but the tail
-  // variant still has an unresolved hand-off race (a few dozen rows of one tile per call come out ~1e-2 off), so
-  // neither is the default.  See DESIGN.md section 7 and profiles/r01_trace_tma_mlp.log.
-  static int use_tma = -1;
-  if (use_tma < 0) {
-    const char* e = getenv("DN_TC_TMA");
-    use_tma = e ? atoi(e) : 0;
-  }
-  bool tma_ok = use_tma != 0 && use_ts != 0 && n_layers > 1 && V < (1ll << 31) && tma_encode_fn() != nullptr;
-  for (int l = 0; l < n_layers; ++l) tma_ok = tma_ok && (layers[l].K % 128 == 0) && (layers[l].N % 32 == 0);
-  // (the 2-layer chain with N1 = 256 runs correctly here too, single accumulator region, but measured slower than
-  //  the split-role kernel below: its layer-1 epilogue cannot overlap the next tile's layer 0)
-  tma_ok = tma_ok && p.nmax == 128;
-  for (int s = 0; s < src.nsrc; ++s) tma_ok = tma_ok && (src.width[s] % T_KS == 0);
-  if (tma_ok) {
-    TcTmaMaps maps;
-    memset(&maps, 0, sizeof(maps));
-    for (int s = 0; s < src.nsrc && tma_ok; ++s)
-      tma_ok = make_row_box_map(&maps.src[s], src.ptr[s], src.width[s], src.ld[s], V, TILE_M) == 0;
-    static int use_tail = -1;
-    if (use_tail < 0) {
-      const char* e = getenv("DN_TC_TMA_TAIL");
-      use_tail = e ? atoi(e) : 0;
-    }
-    const DnLayer& LL = layers[n_layers - 1];
-    if (tma_ok && use_tail && LL.N == 128 && LL.residual && LL.out && !LL.row_scale) {
-      maps.tail = make_row_box_map(&maps.res, LL.residual, LL.N, LL.ld_res, V, TILE_M) == 0 &&
-                  make_row_box_map(&maps.out, LL.out, LL.N, LL.ld_out, V, 32) == 0;
-      for (int l = 0; l + 1 < n_layers; ++l)
-        if (layers[l].out || layers[l].residual) maps.tail = 0;     // (only the last layer goes through the ring)
-    }
-    if (tma_ok) {
-      p.nbuf = (p.nmax == 256) ? 1 : 2;
-      const int grid1 = (int)(ntiles < g_sm_count ? ntiles : g_sm_count);
-      rows_chain_tma_kernel<<<grid1, T_THREADS, T_SMEM, st>>>(p, maps);
-      DN_LAUNCH_CHECK();
-      return DN_OK;
-    }
-  }
   if (use_ts == 1 || (use_ts == 2 && n_layers > 1)) {   // activations in TMEM (A operand read from tensor memory), one CTA per SM
-    const int grid1 = (int)(ntiles < g_sm_count ? ntiles : g_sm_count);
+    const int grid1 = (int)(ntiles < dv->sms ? ntiles : dv->sms);
     rows_chain_ts_kernel<<<grid1, TS_THREADS, TS_SMEM, st>>>(p);
     DN_LAUNCH_CHECK();
     return DN_OK;
   }
-  const int grid = (int)(ntiles < 2 * g_sm_count ? ntiles : 2 * g_sm_count);
+  const int grid = (int)(ntiles < 2 * dv->sms ? ntiles : 2 * dv->sms);
   rows_chain_kernel<<<grid, CHAIN_THREADS, CHAIN_SMEM, st>>>(p);
   DN_LAUNCH_CHECK();
   return DN_OK;
@@ -1660,14 +1189,15 @@ int tc_to_basis_supported(int K, int C) {
 
 int tc_to_basis_partial(const float* values, const float* basis, const float* massvec, int64_t V, int K, int C,
                         float* partial, int* P_out, int passes, cudaStream_t st) {
-  if (!tc_supported_device()) return DN_ERR_NOT_SM100;
+  DevState* dv = cur_dev_state();
+  if (!dv || dv->ok != 1) return DN_ERR_NOT_SM100;
   if ((reinterpret_cast<uintptr_t>(values) & 15) || (reinterpret_cast<uintptr_t>(basis) & 15))
     return DN_ERR_UNSUPPORTED;
   TcToBasisParams p;
   p.values = values; p.basis = basis; p.mass = massvec; p.partial = partial;
-  p.V = V; p.K = K; p.C = C; p.passes = passes; p.variant = env_variant();
+  p.V = V; p.K = K; p.C = C; p.passes = passes;
   const int64_t total_chunks = (V + KC - 1) / KC;
-  int grid = g_sm_count;
+  int grid = dv->sms;
   if (total_chunks < grid) grid = (int)(total_chunks > 0 ? total_chunks : 1);
   p.chunks_per_cta = (total_chunks + grid - 1) / grid;
   if (p.chunks_per_cta < 1) p.chunks_per_cta = 1;

@@ -440,8 +440,13 @@ def spatial_gradient_features_raw(vectors, A_re, A_im):
     return out
 
 
-def block_forward_raw(x_in, mass, evals, evecs, ops, time, A_re, A_im, weights, biases, with_features):
-    """Fused inference forward of one block on one mesh (dn_block_fwd)."""
+PROFILE_STAGES = ("to_basis", "spectral_scale", "pack_weights", "from_basis_pq", "grad_features_gather", "mlp")
+
+
+def block_forward_raw(x_in, mass, evals, evecs, ops, time, A_re, A_im, weights, biases, with_features,
+                      profile=None):
+    """Fused inference forward of one block on one mesh (dn_block_fwd).  ``profile``: a list that receives the
+    per-stage device times in ms (``PROFILE_STAGES`` order; dn_block_fwd_profile, synchronises)."""
     lib = _lib.load()
     x_in, mass, evals, evecs = _f32c(x_in), _f32c(mass), _f32c(evals), _f32c(evecs)
     V, Cc = x_in.shape
@@ -464,6 +469,13 @@ def block_forward_raw(x_in, mass, evals, evecs, ops, time, A_re, A_im, weights, 
     with _on(x_in):
         # the unfused MLP route carves 2 x V x max(hidden) floats: size the scratch by the widest layer
         ws = workspace(V, K, max(Cc, max(dims[1:])), x_in.device)
+        if profile is not None:
+            ms = (C.c_float * 6)()
+            _lib.check(lib.dn_block_fwd_profile(x_in.data_ptr(), mass.data_ptr(), evals.data_ptr(), evecs.data_ptr(),
+                                                csr, C.byref(prm), V, K, Cc, out.data_ptr(), ws.data_ptr(),
+                                                ws.numel(), _engine, _stream(), ms), "dn_block_fwd_profile")
+            profile[:] = [float(v) for v in ms]
+            return out
         _lib.check(lib.dn_block_fwd(x_in.data_ptr(), mass.data_ptr(), evals.data_ptr(), evecs.data_ptr(), csr,
                                     C.byref(prm), V, K, Cc, out.data_ptr(), ws.data_ptr(), ws.numel(), _engine,
                                     _stream()), "dn_block_fwd")

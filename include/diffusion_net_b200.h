@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 2
+#define DN_ABI_VERSION 3
 
 typedef void* dn_stream_t; /* cudaStream_t */
 
@@ -209,6 +209,17 @@ int dn_mini_mlp_bwd(const float* grad_out, const float* const* src_host, const i
 int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const float* evecs,
                  const dn_csr* grad, const dn_block_params* params, int64_t V, int K, int C,
                  float* out, void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream);
+
+/* Profiling hook: the same launch sequence as dn_block_fwd with CUDA events recorded on `stream` between its stages;
+ * SYNCHRONISES on the last event and writes DN_PROFILE_STAGES host floats (milliseconds):
+ *   [0] to_basis (split-V partials)  [1] partial reduction + exp(-lambda t) scale  [2] weight split/pack
+ *   [3] from_basis (+ [P|Q]) chain   [4] sparse gradient gather + inner product + tanh   [5] MiniMLP chain + skip
+ * (bench.py reports each stage's roofline from these).  Not for use inside CUDA-graph capture. */
+#define DN_PROFILE_STAGES 6
+int dn_block_fwd_profile(const float* x_in, const float* mass, const float* evals, const float* evecs,
+                         const dn_csr* grad, const dn_block_params* params, int64_t V, int K, int C,
+                         float* out, void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream,
+                         float* stage_ms_host);
 
 #ifdef __cplusplus
 }
