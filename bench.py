@@ -252,6 +252,8 @@ def main():
     import diffusion_net_b200 as dn
 
     assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU: there is no CPU fallback"
+    # NUMA: bind this rank to its GPU's socket before any pinned buffer exists (e2e scaling over the host link)
+    numa_cpus = dn.dist.bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -311,24 +313,25 @@ def main():
 
     # ---- end to end through the public API from pinned host buffers ----
     pin = lambda t: t.contiguous().pin_memory()
-    gxc, gyc = host_ops[4].coalesce(), host_ops[5].coalesce()
+    # the operator tuple as the framework's host-side form: fp32 arrays + the shared-pattern int32 CSR of
+    # (gradX, gradY) (12 B/nnz; the reference's int64 COO pair is 40 B/nnz).  Everything goes up EVERY step.
+    rp_h, ci_h, gv_h = dn.prepare_operators(gradX, gradY).to_host_csr()
     h = {"x": pin(x_host), "mass": pin(host_ops[0]), "evals": pin(host_ops[2]), "evecs": pin(host_ops[3]),
-         "gi": pin(gxc.indices()), "gxv": pin(gxc.values()), "gyv": pin(gyc.values())}
+         "rowptr": rp_h, "colidx": ci_h, "gvals": gv_h}
     out_host = torch.empty(V, C_WIDTH).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in h.values())
     d2h = out_host.numel() * 4
 
-    def e2e_fn(x, mass, evals, evecs, gi, gxv, gyv):
-        gx = torch.sparse_coo_tensor(gi, gxv, (V, V), is_coalesced=True)
-        gy = torch.sparse_coo_tensor(gi, gyv, (V, V), is_coalesced=True)
+    def e2e_fn(x, mass, evals, evecs, rowptr, colidx, gvals):
+        gops = dn.ops.GradOperators.from_csr(V, rowptr, colidx, gvals)
         with torch.no_grad():
-            return blk(x.unsqueeze(0), mass.unsqueeze(0), None, evals.unsqueeze(0), evecs.unsqueeze(0), [gx], [gy])[0]
+            return blk(x.unsqueeze(0), mass.unsqueeze(0), None, evals.unsqueeze(0), evecs.unsqueeze(0), [gops], None)[0]
 
     # public streaming helper: per step the SAME traffic as the reference's loop (features + the whole
     # operator tuple up, result down; nothing cached across steps), with upload(i+1) / kernels(i) /
     # download(i-1) on three streams
-    pipe = dn.streaming.StreamedForward(e2e_fn, dev, depth=2)
-    out_hosts = [out_host, torch.empty(V, C_WIDTH).pin_memory()]
+    pipe = dn.streaming.StreamedForward(e2e_fn, dev, depth=3)
+    out_hosts = [out_host, torch.empty(V, C_WIDTH).pin_memory(), torch.empty(V, C_WIDTH).pin_memory()]
     for _ in range(3):                                  # warm-up: allocator, CSR prep path, host link
         pipe.result(pipe.submit(h, out_hosts[0]))
     barrier()
@@ -341,7 +344,7 @@ def main():
             a.record(main)
             lastt = None
             for i in range(args.e2e_steps):
-                lastt = pp.submit(hin, out_hosts[i & 1])
+                lastt = pp.submit(hin, out_hosts[i % 3])
             main.wait_event(lastt["fin"])                  # the last result has landed in host memory
             b.record(main)
             pp.drain()
@@ -360,73 +363,79 @@ def main():
     def res_fn(x):
         with torch.no_grad():
             return blk(x.unsqueeze(0), mb, None, eb, vb, [gradX], [gradY])[0]
-    pipe2 = dn.streaming.StreamedForward(res_fn, dev, depth=2)
+    pipe2 = dn.streaming.StreamedForward(res_fn, dev, depth=3)
     for _ in range(2):
         pipe2.result(pipe2.submit({"x": h["x"]}, out_hosts[0]))
     barrier()
     e2e_resident = world * V / (timed_pipe(pipe2, {"x": h["x"]}) * 1e-3) / 1e6
 
-    # ---- per-stage device times (rank 0): which kernel dominates, and its roofline ----
-    roof, stages = None, None
+    # ---- per-stage device times (rank 0) from the SAME launch sequence (dn_block_fwd_profile: CUDA events on the
+    # launching stream between the stages), and the roofline of every kernel of the step ----
+    roof, stages, kernels = None, None, None
     if rank == 0:
         pk = peaks()
+        tf32 = measure_tf32_peak(dev)
         gops = dn.prepare_operators(gradX, gradY)
         A_re, A_im = blk.gradient_features.weights()
         lins = blk.mlp.linears()
-        xd = torch.empty_like(x)
-        feat = torch.empty_like(x)
-
-        def t_ms(fn, n=10):
-            fn()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(n):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / n
-
+        nprof = 10
+        acc = [0.0] * len(dn.ops.PROFILE_STAGES)
         with torch.no_grad():
-            st_to = t_ms(lambda: dn.ops.to_basis_raw(x, evecs, mass))
-            st_diff = t_ms(lambda: dn.ops.DiffusionFn.apply(x, blk.diffusion.diffusion_time, mass, evals, evecs))
-            xd = dn.ops.DiffusionFn.apply(x, blk.diffusion.diffusion_time, mass, evals, evecs)
-            st_gf = t_ms(lambda: dn.ops.GradFeaturesFn.apply(xd, A_re, A_im, gops))
-            feat = dn.ops.GradFeaturesFn.apply(xd, A_re, A_im, gops)
-            st_mlp = t_ms(lambda: dn.ops.mlp_apply([x, xd, feat], [l.weight for l in lins], [l.bias for l in lins],
-                                                   residual=x))
-        stages = {"to_basis_ms": st_to, "diffusion_ms": st_diff, "grad_features_ms": st_gf, "mlp_ms": st_mlp}
-        # dominant kernel: the fused MiniMLP chain (rows_chain_ts_kernel); algorithmic work per vertex:
-        #   flops 10 C^2 (3C->C->C->C), bytes 4*(3C + C) (read x_in,x_diffuse,features; write out)
-        C = C_WIDTH
-        mlp_flops, mlp_bytes = 10 * C * C * V, 4 * 4 * C * V
+            for it in range(nprof + 2):
+                prof = []
+                dn.ops.block_forward_raw(x, mass, evals, evecs, gops, blk.diffusion.diffusion_time, A_re, A_im,
+                                         [l.weight for l in lins], [l.bias for l in lins], True, profile=prof)
+                if it >= 2:
+                    acc = [a + b for a, b in zip(acc, prof)]
+        stages = {n + "_ms": a / nprof for n, a in zip(dn.ops.PROFILE_STAGES, acc)}
+        C, K = C_WIDTH, K_EIG
+        nnz = NNZ_ROW * V
         passes = 3 if args.engine == "tc3x" else 1
-        tf = mlp_flops / (st_mlp * 1e-3) / 1e12                   # algorithmic (useful, fp32-equivalent) flops
-        gbs = mlp_bytes / (st_mlp * 1e-3) / 1e9
-        tf32_peak = pk["bf16_tflops"] / 2.0                        # kind::tf32 runs at half the bf16 MMA rate
-        t_tensor_min = passes * mlp_flops / (tf32_peak * 1e12)     # what the tensor pipe must issue
-        t_hbm_min = mlp_bytes / (pk["hbm_gbs"] * 1e9)
-        if t_tensor_min >= t_hbm_min:
-            roof = {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": tf / pk["bf16_tflops"], "traffic": None,
-                    "issued_tflops": passes * tf, "tf32_peak_assumed": tf32_peak,
-                    "tensor_pipe_frac": passes * tf / tf32_peak}
-        else:
-            roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": gbs / pk["hbm_gbs"], "traffic": None}
-        try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` launch (profiles/)
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-                tj = json.load(fh)["rows_chain_ts_kernel#2"]
-            roof["traffic"] = (tj["dram_read_mb"] + tj["dram_write_mb"]) * 1e6
-            roof["traffic_unit"] = "bytes per launch (algorithmic: {:.0f})".format(mlp_bytes)
+        # algorithmic (minimum) HBM bytes and useful fp32 flops per launch of each kernel
+        work = {
+            "to_basis": (4 * V * (K + C) + 4 * V, 2 * K * C * V, "to_basis_kernel (split-V tcgen05)"),
+            "spectral_scale": (4 * 148 * K * C, 0, "spectral_scale_kernel"),
+            "pack_weights": (3 * 4 * (K * C + 2 * C * C + 5 * C * C), 0, "pack_weights_kernel"),
+            "from_basis_pq": (4 * V * (K + C + 2 * C), (2 * K * C + 4 * C * C) * V,
+                              "rows_chain3_kernel (from_basis -> [P|Q], 2 fused layers)"),
+            "grad_features_gather": (4 * V * (3 * C + C) + 12 * nnz + 4 * V, 12 * NNZ_ROW * C * V,
+                                     "spmm_features_kernel (CSR gather + inner product + tanh)"),
+            "mlp": (4 * V * (3 * C + C), 10 * C * C * V, "rows_chain3_kernel (MiniMLP + skip, 3 fused layers)"),
+        }
+        try:   # per-launch DRAM traffic of each kernel from the committed ncu --set full capture of this command
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
+                traffic = json.load(fh)
         except Exception:
-            pass
-        roof.update({"kernel": "rows_chain_ts_kernel (MiniMLP+skip, 3 fused layers)", "ms": st_mlp, "peak_source": pk["source"],
-                     "issued_flop_factor": passes,
-                     "note": "achieved = algorithmic fp32 flops / CUDA-event time, peak = measured bf16 cuBLAS burst; "
-                             "the kernel issues kind::tf32 MMAs (half the bf16 rate), 3 per product in 3xTF32 mode: "
-                             "tensor_pipe_frac is issued flops over that tf32 rate",
-                     "block_hbm_frac": bytes_per_vertex(K_EIG, C) * V / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"]})
+            traffic = {}
+        kernels = []
+        for name in dn.ops.PROFILE_STAGES:
+            ms = stages[name + "_ms"]
+            by, fl, kname = work[name]
+            gbs = by / (ms * 1e-3) / 1e9
+            tfl = fl / (ms * 1e-3) / 1e12
+            t_hbm = by / (pk["hbm_gbs"] * 1e9)
+            t_tc = passes * fl / (tf32["tf32_tflops"] * 1e12)
+            ent = {"stage": name, "kernel": kname, "ms": ms, "algorithmic_bytes": by, "useful_flops": fl,
+                   "achieved_gbs": gbs, "hbm_frac": gbs / pk["hbm_gbs"],
+                   "issued_tf32_tflops": passes * tfl, "tf32_frac": passes * tfl / tf32["tf32_tflops"],
+                   "bound": "tensor" if t_tc > t_hbm else "hbm", "floor_ms": max(t_tc, t_hbm) * 1e3,
+                   "traffic": traffic.get(name)}
+            kernels.append(ent)
+        dom = max(kernels, key=lambda e: e["ms"])
+        if dom["bound"] == "tensor":
+            roof = {"bound": "tensor", "achieved": dom["issued_tf32_tflops"], "peak": tf32["tf32_tflops"],
+                    "unit": "TFLOP/s", "frac": dom["tf32_frac"],
+                    "note": "kind::tf32 MMAs issued (3 per fp32 product in 3xTF32 mode) over the cuBLAS TF32 GEMM rate "
+                            "measured in this run (burst); useful fp32 flops are a third of `achieved`"}
+        else:
+            roof = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": dom["hbm_frac"],
+                    "note": "algorithmic bytes per launch / CUDA-event time over the measured copy bandwidth"}
+        roof.update({"kernel": dom["kernel"], "ms": dom["ms"], "traffic": dom["traffic"],
+                     "traffic_source": "profiles/r02_traffic.json (one ncu --set full launch of this command)",
+                     "peak_source": pk["source"], "tf32_peak": tf32, "bf16_peak_tflops": pk["bf16_tflops"],
+                     "block_hbm_frac": bytes_per_vertex(K_EIG, C) * V / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+                     "block_tf32_frac": passes * (4 * K * C + 14 * C * C) * V / (ms_step * 1e-3) / 1e12 / tf32["tf32_tflops"]})
 
     # ---- the reference beside it (rank 0, N=1 only; bounded samples) ----
     cpu, gpu_base = None, None
@@ -474,10 +483,11 @@ def main():
                        "min_hbm_mb_per_step": bytes_per_vertex(K_EIG, C_WIDTH) * V / 1e6},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "Mverts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": args.e2e_steps, "pipeline": "StreamedForward depth 2 (upload/compute/download streams)",
+                    "steps": args.e2e_steps, "pipeline": "StreamedForward depth 3 (upload/compute/download streams); operators uploaded every step as fp32 arrays + int32 CSR",
+                    "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None),
                     "operators_resident_value": e2e_resident,
                     "operators_resident_h2d_bytes_per_step": int(h["x"].numel() * 4)},
-            "roofline": roof, "stages_ms": stages, "cpu_baseline": cpu, "gpu_baseline": gpu_base,
+            "roofline": roof, "stages_ms": stages, "kernels": kernels, "cpu_baseline": cpu, "gpu_baseline": gpu_base,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -523,8 +523,6 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
   // (a1) spectral diffusion: to_basis -> exp(-lambda t) -> from_basis   [layers.py:56-67]
   if ((rc = to_basis_partials(x_in, evecs, mass, V, K, C, partial, pf, &P, engine, st))) return rc;
   mark(1);
-  if ((rc = launch_spectral_scale(partial, P, evals, p->diffusion_time, K, C, nullptr, S, 1, st))) return rc;
-  mark(2);
 
   // every dense layer of the block: [0] from_basis, [1] (a5, commuted) [P|Q] = x_diffuse [A_re;A_im]^T,
   // [2..] cat -> MiniMLP -> + x_in  [layers.py:229-239]
@@ -563,13 +561,20 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
                                (tc_rows_chain_supported(src_fb, &L[0], 1) == DN_OK &&
                                 (nfront == 1 || tc_rows_chain_supported(src_pq, &L[1], 1) == DN_OK)));
   const bool tc_mlp = tc && tc_rows_chain_supported(src_mlp, &L[nfront], nm) == DN_OK;
+  // the spectral multiplier S = exp(-lambda t) * (reduced partial sums) is layer 0's weight: when the tensor-core path
+  // takes the front chain it is formed inside the pack launch (no separate scale kernel, S never round-trips HBM)
+  if (!tc_front)
+    if ((rc = launch_spectral_scale(partial, P, evals, p->diffusion_time, K, C, nullptr, S, 1, st))) return rc;
+  mark(2);
   if (tc_front || tc_mlp) {
     DnLayer* first = tc_front ? &L[0] : &L[nfront];
     const int cnt = (tc_front ? nfront : 0) + (tc_mlp ? nm : 0);
     const int64_t pb = tc_chain_ws_bytes(first, cnt);
     float* pk = ws.take(pb / 4);
     if (!pk) return DN_ERR_WORKSPACE;
-    if ((rc = tc_pack_layers(first, cnt, pk, pb, st))) return rc;
+    if (tc_front) rc = tc_pack_layers_spectral(first, cnt, pk, pb, partial, P, evals, p->diffusion_time, 1, st);
+    else rc = tc_pack_layers(first, cnt, pk, pb, st);
+    if (rc) return rc;
   }
   mark(3);
   float *t0 = nullptr, *t1 = nullptr;

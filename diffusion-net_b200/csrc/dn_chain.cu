@@ -46,13 +46,14 @@ constexpr int C3_THREADS = 512;
 constexpr int C3_KS = 32;                       // k-columns per pipeline stage
 constexpr int C3_TILE = 128;                    // rows per tile == UMMA M
 constexpr int C3_RAW = C3_TILE * C3_KS * 4;     // 16 KiB row box
-constexpr int C3_NR = 4;                        // row-box slots (slot r & 3; slots of one parity belong to one warpgroup)
-constexpr int C3_NOUT = 2;                      // output staging buffers (128 rows x 32 columns each)
+// row-box slots + output staging buffers share 6 x 16 KiB: 4 + 2 (default: layer 0 is long, the output is short) or
+// 2 + 4 (from_basis -> [P|Q]: four layer-0 stages per tile, 192 KiB of output per tile)
+constexpr int C3_IO_BUFS = 6;
 constexpr int C3_WBYTES = 131072;               // weight ring
-constexpr int C3_OFF_OUT = C3_NR * C3_RAW;
-constexpr int C3_OFF_W = C3_OFF_OUT + C3_NOUT * C3_RAW;
+constexpr int C3_OFF_W = C3_IO_BUFS * C3_RAW;
 constexpr int C3_OFF_BAR = C3_OFF_W + C3_WBYTES;
-constexpr int C3_SMEM = C3_OFF_BAR + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int C3_BIAS_FLOATS = 512;             // biases of all layers, staged once (sum of N over the layers that have one)
+constexpr int C3_SMEM = C3_OFF_BAR + 512 /*barriers*/ + C3_BIAS_FLOATS * 4;
 
 struct C3Layer {
   const float* wpack;      // tc_pack_layers layout (16-wide chunks of [hi | lo] images)
@@ -69,6 +70,8 @@ struct C3Params {
   int nbuf;        // accumulator buffers (2: ping-pong, column 128 * (g & 1); 1: column 0)
   int ring_col;    // first TMEM column of the operand ring
   int ns_shift;    // log2(ring depth): 2 -> 4 stages (32 KiB weight slots), 1 -> 2 stages (64 KiB weight slots)
+  int nr_shift;    // log2(row-box slots): 2 or 1;  output staging buffers = 6 - slots
+  int bias_smem;   // biases fit the staging area (else the epilogues read them with __ldg)
   int64_t V;
   long long* trace;   // optional (tools/trace_chain3.py): per-warp (event, clock64) pairs of CTA 0
 };
@@ -138,11 +141,14 @@ __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, fl
 
 __global__ void __launch_bounds__(C3_THREADS, 1)
 rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C3Maps maps) {
-  extern __shared__ uint8_t smem_raw_[];
-  const uint32_t smem0 = (smem_u32(smem_raw_) + 1023u) & ~1023u;        // SWIZZLE_128B boxes need 1024 B alignment
-  uint8_t* smem = smem_raw_ + (smem0 - smem_u32(smem_raw_));
-  const uint32_t raw_u = smem0, out_u = smem0 + C3_OFF_OUT, w_u = smem0 + C3_OFF_W;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem0 = smem_u32(smem);
+  if (smem0 & 1023u) __trap();                                          // SWIZZLE_128B boxes need 1024 B alignment
+  const uint32_t nr_sh = (uint32_t)p.nr_shift, nr_mask = (1u << nr_sh) - 1u;
+  const uint32_t nout = (uint32_t)C3_IO_BUFS - (1u << nr_sh), nout_mask = nout - 1u;   // 2 or 4
+  const uint32_t raw_u = smem0, out_u = smem0 + ((uint32_t)C3_RAW << nr_sh), w_u = smem0 + C3_OFF_W;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C3_OFF_BAR);
+  float* sbias = reinterpret_cast<float*>(smem + C3_OFF_BAR + 512);
   // bars: raw_full[4] raw_empty[4] full[4] ab_empty[4] dm_full[2] do_full[2] dm_empty[2] do_empty[2] res[4 warps][2] done
   //   full[s]     : operand stage s AND weight stage s are ready (4 operand-warp arrivals + the weight producer's
   //                 arrive.expect_tx): the MMA warp waits once per stage
@@ -155,8 +161,8 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
   const uint32_t full = smem_u32(bars + 8), ab_empty = smem_u32(bars + 12);
   const uint32_t dm_full = smem_u32(bars + 16), do_full = smem_u32(bars + 18);
   const uint32_t dm_empty = smem_u32(bars + 20), do_empty = smem_u32(bars + 22);
-  const uint32_t res_bar = smem_u32(bars + 24), done_bar = smem_u32(bars + 32);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+  const uint32_t res_bar = smem_u32(bars + 24), done_bar = smem_u32(bars + 40);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tr_n = 0;
@@ -169,13 +175,22 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
       mbar_init(dm_full + 8 * i, 1);  mbar_init(do_full + 8 * i, 1);
       mbar_init(dm_empty + 8 * i, 8); mbar_init(do_empty + 8 * i, 4);
     }
-    for (int i = 0; i < 4 * C3_NOUT; ++i) mbar_init(res_bar + 8 * i, 1);
+    for (int i = 0; i < 16; ++i) mbar_init(res_bar + 8 * i, 1);
     mbar_init(done_bar, 1);
     fence_barrier_init();
   }
   if (warp == 3) tmem_alloc<512>(smem_u32(tmem_slot));
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.nsrc; ++s) prefetch_tmap(&maps.src[s]);
+  }
+  if (p.bias_smem) {                       // layer l's bias at sbias[sum of N over earlier layers]
+    int off = 0;
+    for (int l = 0; l < p.n_layers; ++l) {
+      const int N = p.layer[l].N;
+      if (p.layer[l].bias)
+        for (int i = threadIdx.x; i < N; i += blockDim.x) sbias[off + i] = __ldg(p.layer[l].bias + i);
+      off += N;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -215,9 +230,9 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int s = 0, k0 = 0;
       for (int c = 0; c < nst0; ++c, ++r) {
-        const uint32_t sl = r & 3u;
+        const uint32_t sl = r & nr_mask;
         C3_TRACE(50);
-        mbar_wait(raw_empty + 8 * sl, ((r >> 2) & 1) ^ 1);
+        mbar_wait(raw_empty + 8 * sl, ((r >> nr_sh) & 1) ^ 1);
         C3_TRACE(51);
         if (elect_one()) {
           mbar_arrive_expect_tx(raw_full + 8 * sl, C3_RAW);
@@ -255,12 +270,16 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         }
         tc_fence_after();
         C3_TRACE(24);
+        uint32_t ready = 0;                                   // this stage's barrier was already seen complete
         for (int c = 0; c < nst; ++c, ++i) {
           const uint32_t s = i & ns_mask, ph = (i >> ns_sh) & 1u;
           C3_TRACE(20);
-          mbar_wait(full + 8 * s, ph);
+          if (!ready) mbar_wait(full + 8 * s, ph);
           C3_TRACE(21);
           tc_fence_after();
+          // probe the next stage while this one is issued: a completed barrier then costs nothing on the way round
+          ready = (c + 1 < nst) ? mbar_test(full + 8 * ((i + 1) & ns_mask), ((i + 1) >> ns_sh) & 1u) : 0u;
+          ready = __all_sync(0xffffffffu, ready != 0) ? 1u : 0u;     // every lane observed it (acquire per lane)
           if (elect_one()) {
             const uint32_t a0 = tmem_base + (uint32_t)p.ring_col + s * 64u;
             const uint64_t dbs = tmplB + (w_u4 + s * (w_slot >> 4));
@@ -328,13 +347,14 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
     uint32_t um0 = 0, um1 = 0;                          // chained-epilogue uses of accumulator buffer 0 / 1 so far
     int S = 0;
     for (int l = 0; l < L; ++l) S += p.layer[l].K / C3_KS;
+    const bool bsm = p.bias_smem != 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_seq) {
       const uint32_t i_base = t_seq * (uint32_t)S, r_base = t_seq * (uint32_t)nst0;
       // ---- layer 0: my stages of the row boxes -> TMEM
       for (int c = (int)wg; c < nst0; c += 2) {
-        const uint32_t r = r_base + (uint32_t)c, sl = r & 3u;
+        const uint32_t r = r_base + (uint32_t)c, sl = r & nr_mask;
         C3_TRACE(1);
-        mbar_wait(raw_full + 8 * sl, (r >> 2) & 1u);
+        mbar_wait(raw_full + 8 * sl, (r >> nr_sh) & 1u);
         C3_TRACE(2);
         const uint32_t rowaddr = raw_u + sl * C3_RAW + (uint32_t)trow * 128u;
         float x[32];
@@ -365,6 +385,8 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         tc_fence_after();
         const uint32_t d_lane = lane_base + buf * 128u;
         bool released = false;
+        int boff = 0;
+        for (int q = 0; q < l; ++q) boff += p.layer[q].N;
         for (int c = (int)wg; c < nco; c += 2) {
           float v[32];
           tmem_ld32(d_lane + (uint32_t)c * C3_KS, v);
@@ -376,10 +398,11 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
             released = true;
           }
           if (Lr.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(Lr.bias + c * C3_KS);
+            const float4* bp = bsm ? reinterpret_cast<const float4*>(sbias + boff + c * C3_KS)
+                                   : reinterpret_cast<const float4*>(Lr.bias + c * C3_KS);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(bp + j);
+              const float4 b = bp[j];                      // (broadcast LDS when staged)
               v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
           }
@@ -403,9 +426,10 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
     const int trow = 32 * quarter + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * quarter) << 16);
     const uint32_t swz = (uint32_t)(lane & 7);                   // slices start on a 1024 B boundary: row-in-slice & 7
-    const uint32_t my_res = res_bar + 8u * (uint32_t)(quarter * C3_NOUT);
-    uint32_t oc = 0;                 // output chunks issued so far (staging buffer = oc & 1)
-    uint32_t rc0 = 0, rc1 = 0;       // residual loads waited so far per staging buffer
+    const uint32_t my_res = res_bar + 8u * (uint32_t)(quarter * 4);
+    uint32_t oc = 0;                 // output chunks issued so far (staging buffer = oc mod nout)
+    uint32_t rcbits = 0;             // bit b: parity of the residual loads waited so far on staging buffer b
+    const bool bsm = p.bias_smem != 0;
     uint32_t uo0 = 0, uo1 = 0;       // output uses of accumulator buffer 0 / 1 so far
     uint32_t t_seq = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_seq) {
@@ -422,20 +446,22 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         const bool res = Lr.has_res != 0;
         const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
         const uint32_t d_lane = lane_base + buf * 128u;
+        int boff = 0;
+        for (int q = 0; q < l; ++q) boff += p.layer[q].N;
         C3_TRACE(30);
         if (!res) {
           mbar_wait(do_full + 8 * buf, use & 1u);
           tc_fence_after();
           C3_TRACE(31);
         }
-        for (int c0 = 0; c0 < nco; c0 += C3_NOUT) {
-          const int ng = (nco - c0) < C3_NOUT ? (nco - c0) : C3_NOUT;
+        for (int c0 = 0; c0 < nco; c0 += (int)nout) {
+          const int ng = (nco - c0) < (int)nout ? (nco - c0) : (int)nout;
           if (res) {
             // this group's residual slices: fetched by TMA into the staging slices the results will overwrite
             if (lane == 0) {
               bulk_wait_read<0>();                               // every earlier store has left its slice
               for (int j = 0; j < ng; ++j) {
-                const uint32_t b = (oc + (uint32_t)j) & 1u;
+                const uint32_t b = (oc + (uint32_t)j) & nout_mask;
                 mbar_arrive_expect_tx(my_res + 8 * b, 4096);
                 tma_box_load(out_u + b * C3_RAW + (uint32_t)quarter * 4096u, &maps.res, (c0 + j) * C3_KS, row0,
                              my_res + 8 * b);
@@ -450,10 +476,12 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
           }
           for (int j = 0; j < ng; ++j, ++oc) {
             const int c = c0 + j;
-            const uint32_t b = oc & 1u;
+            const uint32_t b = oc & nout_mask;
             const uint32_t slice = out_u + b * C3_RAW + (uint32_t)quarter * 4096u;
             if (!res) {
-              if (lane == 0) bulk_wait_read<C3_NOUT - 1>();      // the store that last used this slice has read it
+              if (lane == 0) {                                   // the store that last used this slice has read it
+                if (nout == 4) bulk_wait_read<3>(); else bulk_wait_read<1>();
+              }
               __syncwarp();
             }
             C3_TRACE(32);
@@ -466,10 +494,11 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
               if (lane == 0) mbar_arrive(do_empty + 8 * buf);
             }
             if (Lr.bias) {
-              const float4* bp = reinterpret_cast<const float4*>(Lr.bias + c * C3_KS);
+              const float4* bp = bsm ? reinterpret_cast<const float4*>(sbias + boff + c * C3_KS)
+                                     : reinterpret_cast<const float4*>(Lr.bias + c * C3_KS);
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
-                const float4 bb = __ldg(bp + jj);
+                const float4 bb = bp[jj];
                 v[4 * jj] += bb.x; v[4 * jj + 1] += bb.y; v[4 * jj + 2] += bb.z; v[4 * jj + 3] += bb.w;
               }
             }
@@ -483,9 +512,9 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
             }
             const uint32_t rowaddr = slice + (uint32_t)lane * 128u;
             if (res) {
-              mbar_wait(my_res + 8 * b, (b ? rc1 : rc0) & 1u);
+              mbar_wait(my_res + 8 * b, (rcbits >> b) & 1u);
               C3_TRACE(34);
-              if (b) ++rc1; else ++rc0;
+              rcbits ^= (1u << b);
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
                 const float4 q = lds128(rowaddr + ((((uint32_t)jj) ^ swz) << 4));
@@ -635,6 +664,20 @@ int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, in
   if (nmax <= 128) { p.nbuf = 2; p.ring_col = 256; p.ns_shift = 2; }
   else if (n_layers == 2) { p.nbuf = 2; p.ring_col = 384; p.ns_shift = 1; }
   else { p.nbuf = 1; p.ring_col = 256; p.ns_shift = 1; }
+  // output-heavy chains (few layer-0 stages per tile, many output columns): 2 row-box slots + 4 staging buffers
+  int out_cols = 0, bias_floats = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    if (layers[l].out) out_cols += layers[l].N;
+    bias_floats += layers[l].N;
+  }
+  p.nr_shift = (out_cols > layers[0].K) ? 1 : 2;
+  {
+    static int nr_env = -2;
+    if (nr_env == -2) { const char* e = getenv("DN_C3_NR"); nr_env = e ? atoi(e) : -1; }
+    if (nr_env == 2) p.nr_shift = 1;
+    if (nr_env == 4) p.nr_shift = 2;
+  }
+  p.bias_smem = bias_floats <= C3_BIAS_FLOATS ? 1 : 0;
   const int64_t ntiles = (V + C3_TILE - 1) / C3_TILE;
   const int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
   rows_chain3_kernel<<<grid, C3_THREADS, C3_SMEM, st>>>(p, maps);

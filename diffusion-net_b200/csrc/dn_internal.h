@@ -103,3 +103,7 @@ int tc_to_basis_supported(int K, int C);
 int64_t tc_chain_ws_bytes(const DnLayer* layers, int n_layers);
 // one launch: pack the weights of n layers into ws and set layers[i].prepacked
 int tc_pack_layers(DnLayer* layers, int n_layers, void* ws, int64_t ws_bytes, cudaStream_t st);
+// same, with layers[0] (w_trans, K = eigen count, N = channels) replaced by the spectral multiplier
+//   S[k][n] = exp(-evals[k] * max(time[n], 1e-8)) * sum_p partial[p][k][n]    (one launch for scale + pack)
+int tc_pack_layers_spectral(DnLayer* layers, int n_layers, void* ws, int64_t ws_bytes, const float* partial, int P,
+                            const float* evals, float* time, int clamp_writeback, cudaStream_t st);

@@ -356,6 +356,15 @@ struct Acc4 {
   float4 gX, gY, bre, bim;
 };
 
+// tanh(x) = 1 - 2 / (exp(2x) + 1) with the hardware exp2 and fast division: ~6 instructions instead of tanhf's ~30
+// (the gather kernel issues instructions on 53 % of its cycles, profiles/r01: the four tanhf per lane were a fifth of
+// them).  Absolute error <= ~1.5e-7 over the whole range (saturates to +-1, NaN propagates); every gather variant
+// uses this one function so that they stay bit-identical to each other.
+__device__ __forceinline__ float feat_tanh(float x) {
+  const float e = __expf(2.f * x);
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+
 template <bool ROT>
 __device__ __forceinline__ Acc4 gather_row(const int32_t* __restrict__ colidx, const float2* __restrict__ vals,
                                            const float* __restrict__ xd, const float* __restrict__ pq, int ld_pq,
@@ -404,11 +413,132 @@ __global__ void __launch_bounds__(256) spmm_features_kernel(const int32_t* __res
   for (int c4 = gl; c4 < (C >> 2); c4 += G) {
     const Acc4 a = gather_row<ROT>(colidx, vals, xd, pq, ld_pq, C, s, e, c4);
     float4 o;
-    o.x = tanhf(fmaf(a.gX.x, a.bre.x, a.gY.x * a.bim.x));
-    o.y = tanhf(fmaf(a.gX.y, a.bre.y, a.gY.y * a.bim.y));
-    o.z = tanhf(fmaf(a.gX.z, a.bre.z, a.gY.z * a.bim.z));
-    o.w = tanhf(fmaf(a.gX.w, a.bre.w, a.gY.w * a.bim.w));
+    o.x = feat_tanh(fmaf(a.gX.x, a.bre.x, a.gY.x * a.bim.x));
+    o.y = feat_tanh(fmaf(a.gX.y, a.bre.y, a.gY.y * a.bim.y));
+    o.z = feat_tanh(fmaf(a.gX.z, a.bre.z, a.gY.z * a.bim.z));
+    o.w = feat_tanh(fmaf(a.gX.w, a.bre.w, a.gY.w * a.bim.w));
     *reinterpret_cast<float4*>(feat + row * C + c4 * 4) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Default gather at C = 128: persistent warps, 16 consecutive rows per warp visit, software-pipelined metadata,
+// packed fp32x2 FMAs.
+//   * the round-1 kernel (one short-lived warp per row) issued ~530 warp instructions per row and spent 53 % of its
+//     cycles issuing: here the 24 FFMA per (neighbour, float4) become 12 FFMA2 (fma.rn.f32x2 -- two IEEE fp32 FMAs per
+//     instruction, bit-identical results), tanhf becomes feat_tanh, and P, Q share one address computation;
+//   * a row's (col, gx, gy) triples are fetched by the lanes in ONE coalesced load each, one row ahead of use, and
+//     broadcast with shuffles: the neighbour-row gathers never wait on a dependent index load;
+//   * a warp walks 16 consecutive rows, so a row re-reads most of its predecessor's neighbour rows out of L1.
+// Entry order = CSR order and the arithmetic per element is the same fmaf sequence as gather_row.
+// ---------------------------------------------------------------------------------------------
+constexpr int GP_ROWS = 16;     // consecutive rows per warp visit
+
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// d = a * b + d on both fp32 halves (sm_100 FFMA2)
+__device__ __forceinline__ void fma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
+// GP_NB: neighbour rows gathered per batch (3 * GP_NB independent 16-byte loads per lane); MINB: CTAs per SM the
+// register budget is sized for
+template <bool ROT, int GP_NB, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+spmm_features_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                          const float2* __restrict__ vals, const float* __restrict__ xd,
+                          const float* __restrict__ pq, int ld_pq, int64_t V, float* __restrict__ feat) {
+  constexpr int C = 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t nblk = (V + GP_ROWS - 1) / GP_ROWS;
+  const char* xb = reinterpret_cast<const char*>(xd) + lane * 16;
+  const char* pb = reinterpret_cast<const char*>(pq) + lane * 16;
+  const int64_t pq_row_bytes = (int64_t)ld_pq * 4;
+  for (int64_t blk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < nblk; blk += nwarps) {
+    const int64_t base = blk * GP_ROWS;
+    const int nrows = (int)((V - base) < GP_ROWS ? (V - base) : GP_ROWS);
+    // rowptr[base .. base+16] held by lanes 0..16
+    const int rp = (lane <= nrows) ? __ldg(rowptr + base + lane) : 0;
+    int s = __shfl_sync(0xffffffffu, rp, 0), e = __shfl_sync(0xffffffffu, rp, 1);
+    int mycol = 0;
+    float2 myg = make_float2(0.f, 0.f);
+    if (lane < e - s) { mycol = __ldg(colidx + s + lane); myg = __ldg(vals + s + lane); }
+    for (int r = 0; r < nrows; ++r) {
+      const int n = e - s;
+      // next row's triples: in flight while this row is gathered
+      int s2 = 0, e2 = 0, col2 = 0;
+      float2 g2 = make_float2(0.f, 0.f);
+      if (r + 1 < nrows) {
+        s2 = __shfl_sync(0xffffffffu, rp, r + 1);
+        e2 = __shfl_sync(0xffffffffu, rp, r + 2);
+        if (lane < e2 - s2) { col2 = __ldg(colidx + s2 + lane); g2 = __ldg(vals + s2 + lane); }
+      }
+      unsigned long long gX0 = 0ull, gX1 = 0ull, gY0 = 0ull, gY1 = 0ull, re0 = 0ull, re1 = 0ull, im0 = 0ull, im1 = 0ull;
+      for (int b0 = 0; b0 < n; b0 += 32) {                       // rows longer than a warp: 32 entries at a time
+        int col_l = mycol;
+        float2 g_l = myg;
+        if (b0 > 0) {
+          col_l = 0; g_l = make_float2(0.f, 0.f);
+          if (b0 + lane < n) { col_l = __ldg(colidx + s + b0 + lane); g_l = __ldg(vals + s + b0 + lane); }
+        }
+        const int cnt = (n - b0) < 32 ? (n - b0) : 32;
+        for (int p0 = 0; p0 < cnt; p0 += GP_NB) {
+          ulonglong2 x[GP_NB], P[GP_NB], Q[GP_NB];
+          float wx[GP_NB], wy[GP_NB];
+#pragma unroll
+          for (int j = 0; j < GP_NB; ++j) {
+            const int pj = (p0 + j < cnt) ? p0 + j : p0;
+            const int64_t col = __shfl_sync(0xffffffffu, col_l, pj);
+            wx[j] = __shfl_sync(0xffffffffu, g_l.x, pj);
+            wy[j] = __shfl_sync(0xffffffffu, g_l.y, pj);
+            if (p0 + j < cnt) {
+              x[j] = __ldg(reinterpret_cast<const ulonglong2*>(xb + col * (C * 4)));
+              const char* pr = pb + col * pq_row_bytes;
+              P[j] = __ldg(reinterpret_cast<const ulonglong2*>(pr));
+              if (ROT) Q[j] = __ldg(reinterpret_cast<const ulonglong2*>(pr + C * 4));
+            } else {
+              x[j] = make_ulonglong2(0ull, 0ull); P[j] = x[j]; Q[j] = x[j];
+              wx[j] = 0.f; wy[j] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < GP_NB; ++j) {
+            if (p0 + j < cnt) {                                    // (warp-uniform)
+              const unsigned long long gx2 = pack2(wx[j], wx[j]), gy2 = pack2(wy[j], wy[j]);
+              fma2(gX0, gx2, x[j].x); fma2(gX1, gx2, x[j].y);
+              fma2(gY0, gy2, x[j].x); fma2(gY1, gy2, x[j].y);
+              fma2(re0, gx2, P[j].x); fma2(re1, gx2, P[j].y);
+              fma2(im0, gy2, P[j].x); fma2(im1, gy2, P[j].y);
+              if (ROT) {
+                const unsigned long long ngy2 = pack2(-wy[j], -wy[j]);
+                fma2(re0, ngy2, Q[j].x); fma2(re1, ngy2, Q[j].y);
+                fma2(im0, gx2, Q[j].x); fma2(im1, gx2, Q[j].y);
+              }
+            }
+          }
+        }
+      }
+      float gXv[4], gYv[4], rev[4], imv[4];
+      unpack2(gX0, gXv[0], gXv[1]); unpack2(gX1, gXv[2], gXv[3]);
+      unpack2(gY0, gYv[0], gYv[1]); unpack2(gY1, gYv[2], gYv[3]);
+      unpack2(re0, rev[0], rev[1]); unpack2(re1, rev[2], rev[3]);
+      unpack2(im0, imv[0], imv[1]); unpack2(im1, imv[2], imv[3]);
+      float4 o;
+      o.x = feat_tanh(fmaf(gXv[0], rev[0], gYv[0] * imv[0]));
+      o.y = feat_tanh(fmaf(gXv[1], rev[1], gYv[1] * imv[1]));
+      o.z = feat_tanh(fmaf(gXv[2], rev[2], gYv[2] * imv[2]));
+      o.w = feat_tanh(fmaf(gXv[3], rev[3], gYv[3] * imv[3]));
+      *reinterpret_cast<float4*>(feat + (base + r) * C + lane * 4) = o;
+      s = s2; e = e2; mycol = col2; myg = g2;
+    }
   }
 }
 
@@ -514,10 +644,10 @@ __global__ void __launch_bounds__(512) spmm_features_patch_kernel(const dn_patch
         }
       }
       float4 o;
-      o.x = tanhf(fmaf(a.gX.x, a.bre.x, a.gY.x * a.bim.x));
-      o.y = tanhf(fmaf(a.gX.y, a.bre.y, a.gY.y * a.bim.y));
-      o.z = tanhf(fmaf(a.gX.z, a.bre.z, a.gY.z * a.bim.z));
-      o.w = tanhf(fmaf(a.gX.w, a.bre.w, a.gY.w * a.bim.w));
+      o.x = feat_tanh(fmaf(a.gX.x, a.bre.x, a.gY.x * a.bim.x));
+      o.y = feat_tanh(fmaf(a.gX.y, a.bre.y, a.gY.y * a.bim.y));
+      o.z = feat_tanh(fmaf(a.gX.z, a.bre.z, a.gY.z * a.bim.z));
+      o.w = feat_tanh(fmaf(a.gX.w, a.bre.w, a.gY.w * a.bim.w));
       *reinterpret_cast<float4*>(feat + cur.row * C + c4 * 4) = o;
     }
     cur = nxt;
@@ -627,10 +757,10 @@ spmm_features_patch_async_kernel(const dn_patches P, const float* __restrict__ x
           }
         }
         float4 o;
-        o.x = tanhf(fmaf(a.gX.x, a.bre.x, a.gY.x * a.bim.x));
-        o.y = tanhf(fmaf(a.gX.y, a.bre.y, a.gY.y * a.bim.y));
-        o.z = tanhf(fmaf(a.gX.z, a.bre.z, a.gY.z * a.bim.z));
-        o.w = tanhf(fmaf(a.gX.w, a.bre.w, a.gY.w * a.bim.w));
+        o.x = feat_tanh(fmaf(a.gX.x, a.bre.x, a.gY.x * a.bim.x));
+        o.y = feat_tanh(fmaf(a.gX.y, a.bre.y, a.gY.y * a.bim.y));
+        o.z = feat_tanh(fmaf(a.gX.z, a.bre.z, a.gY.z * a.bim.z));
+        o.w = feat_tanh(fmaf(a.gX.w, a.bre.w, a.gY.w * a.bim.w));
         *reinterpret_cast<float4*>(feat + cur.row * C + c4 * 4) = o;
       }
       cur = nxt;
@@ -700,10 +830,10 @@ __global__ void __launch_bounds__(256) spmm_features_v2_kernel(const int32_t* __
       }
     }
     float4 o;
-    o.x = tanhf(fmaf(gX.x, bre.x, gY.x * bim.x));
-    o.y = tanhf(fmaf(gX.y, bre.y, gY.y * bim.y));
-    o.z = tanhf(fmaf(gX.z, bre.z, gY.z * bim.z));
-    o.w = tanhf(fmaf(gX.w, bre.w, gY.w * bim.w));
+    o.x = feat_tanh(fmaf(gX.x, bre.x, gY.x * bim.x));
+    o.y = feat_tanh(fmaf(gX.y, bre.y, gY.y * bim.y));
+    o.z = feat_tanh(fmaf(gX.z, bre.z, gY.z * bim.z));
+    o.w = feat_tanh(fmaf(gX.w, bre.w, gY.w * bim.w));
     *reinterpret_cast<float4*>(feat + row * C + c4 * 4) = o;
   }
 }
@@ -959,6 +1089,31 @@ int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int 
     }
   }
   const float2* vals = reinterpret_cast<const float2*>(g->vals);
+  static int use_pipe = -1;
+  if (use_pipe < 0) {
+    const char* e = getenv("DN_SPMM_PIPE");
+    use_pipe = e ? atoi(e) : 1;
+  }
+  if (C == 128 && use_pipe) {
+    int dev = 0, nsm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t nblk = (V + GP_ROWS - 1) / GP_ROWS;
+    const int ld = rotations ? 2 * C : C;
+    // use_pipe: 1 = 4 neighbours per batch, 2 CTAs/SM (no spills) | 2 = 2 per batch, 4 CTAs/SM | 3 = 3 per batch, 3 CTAs/SM
+    const int minb = use_pipe == 2 ? 4 : (use_pipe == 3 ? 3 : 2);
+    int64_t ctas = (nblk + 7) / 8;
+    if (ctas > (int64_t)minb * nsm) ctas = (int64_t)minb * nsm;
+#define DN_PIPE_LAUNCH(ROT_, NB_, MB_) \
+    spmm_features_pipe_kernel<ROT_, NB_, MB_><<<(unsigned)ctas, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, feat)
+    if (rotations) {
+      if (use_pipe == 2) DN_PIPE_LAUNCH(true, 2, 4); else if (use_pipe == 3) DN_PIPE_LAUNCH(true, 3, 3); else DN_PIPE_LAUNCH(true, 4, 2);
+    } else {
+      if (use_pipe == 2) DN_PIPE_LAUNCH(false, 2, 4); else if (use_pipe == 3) DN_PIPE_LAUNCH(false, 3, 3); else DN_PIPE_LAUNCH(false, 4, 2);
+    }
+#undef DN_PIPE_LAUNCH
+    DN_LAUNCH_CHECK();
+    return DN_OK;
+  }
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("DN_SPMM_VARIANT");

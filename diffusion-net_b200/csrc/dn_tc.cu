@@ -72,6 +72,12 @@ struct PackJob {
 struct PackJobs {
   PackJob j[DN_MAX_LAYERS];
   int n, kc;
+  // optional: job 0's matrix is the spectral multiplier S[k][n] = exp(-evals[k] * max(t[n], 1e-8)) * sum_p partial[p][k][n]
+  // (layers.py:48-49, 62-64), formed here instead of by a separate launch; the clamped time is written back in place
+  const float* sp_partial;
+  const float* sp_evals;
+  float* sp_time;
+  int sp_P, sp_clamp;
 };
 
 // all weight matrices of a block forward in one launch (blocks are assigned to jobs by blk0)
@@ -84,11 +90,25 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackJobs jobs) {
   const int idx = ((int)blockIdx.x - J.blk0) * blockDim.x + threadIdx.x;
   if (idx >= J.K * J.N) return;
   const int K = J.K, N = J.N, kc = jobs.kc;
-  const int n = idx / K, k = idx % K;
+  int n, k;
   float w;
-  if (J.w_trans) w = J.W[(int64_t)k * J.ldw + n];
-  else if (J.W2 && n >= J.n_split) w = J.W2[(int64_t)(n - J.n_split) * J.ldw + k];
-  else w = J.W[(int64_t)n * J.ldw + k];
+  if (ji == 0 && jobs.sp_partial) {
+    k = idx / N; n = idx % N;                               // n fastest: coalesced reads of the partial sums
+    float acc0 = 0.f, acc1 = 0.f;
+    const float* pp = jobs.sp_partial + idx;
+    const int64_t stride = (int64_t)K * N;
+    int q = 0;
+    for (; q + 1 < jobs.sp_P; q += 2) { acc0 += pp[(int64_t)q * stride]; acc1 += pp[(int64_t)(q + 1) * stride]; }
+    if (q < jobs.sp_P) acc0 += pp[(int64_t)q * stride];
+    const float t = fmaxf(jobs.sp_time[n], 1e-8f);         // torch.clamp(t, min=1e-8)
+    w = expf(-(jobs.sp_evals[k] * t)) * (acc0 + acc1);
+    if (jobs.sp_clamp && k == K - 1) jobs.sp_time[n] = t;   // (idempotent for the other readers of t[n])
+  } else {
+    n = idx / K; k = idx % K;
+    if (J.w_trans) w = J.W[(int64_t)k * J.ldw + n];
+    else if (J.W2 && n >= J.n_split) w = J.W2[(int64_t)(n - J.n_split) * J.ldw + k];
+    else w = J.W[(int64_t)n * J.ldw + k];
+  }
   float hi, lo;
   split_tf32(w, hi, lo);
   const int chunk = k / kc, kk = k % kc;
@@ -1089,10 +1109,16 @@ int64_t tc_chain_ws_bytes(const DnLayer* layers, int n_layers) {
 }
 
 int tc_pack_layers(DnLayer* layers, int n_layers, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  return tc_pack_layers_spectral(layers, n_layers, ws, ws_bytes, nullptr, 0, nullptr, nullptr, 0, st);
+}
+
+int tc_pack_layers_spectral(DnLayer* layers, int n_layers, void* ws, int64_t ws_bytes, const float* partial, int P,
+                            const float* evals, float* time, int clamp_writeback, cudaStream_t st) {
   if (n_layers < 1 || n_layers > DN_MAX_LAYERS) return DN_ERR_INVALID_ARGUMENT;
   if (tc_chain_ws_bytes(layers, n_layers) > ws_bytes || !ws) return DN_ERR_WORKSPACE;
   PackJobs jobs;
   memset(&jobs, 0, sizeof(jobs));
+  jobs.sp_partial = partial; jobs.sp_P = P; jobs.sp_evals = evals; jobs.sp_time = time; jobs.sp_clamp = clamp_writeback;
   jobs.n = n_layers;
   jobs.kc = KC;
   char* wp = static_cast<char*>(ws);

@@ -175,7 +175,11 @@ class DiffusionNetBlock(nn.Module):
         gops = [None] * B
         if self.with_gradient_features:
             if isinstance(gradX, (list, tuple)):           # pre-split per-mesh operators
-                gops = [ops.prepare_operators(gx, gy) for gx, gy in zip(gradX, gradY)]
+                # an element may already be a prepared ops.GradOperators (geometry.get_operators /
+                # GradOperators.from_csr): it then stands for the (gradX, gradY) pair and gradY[b] is ignored
+                gys = gradY if gradY is not None else [None] * len(gradX)
+                gops = [gx if isinstance(gx, ops.GradOperators) else ops.prepare_operators(gx, gy)
+                        for gx, gy in zip(gradX, gys)]
             else:
                 gops = ops.prepare_operators_batched(gradX, gradY)
         params_need_grad = any(p.requires_grad for p in self.parameters())

@@ -142,6 +142,33 @@ class GradOperators:
         self._coo = None
         return self
 
+    @classmethod
+    def from_csr(cls, V, rowptr, colidx, vals_xy):
+        """Wrap an already-built shared-pattern CSR that lives on the device: ``rowptr`` int32 (V+1), ``colidx`` int32
+        (nnz), ``vals_xy`` float32 (nnz, 2) = (gradX, gradY) values interleaved.  No kernel runs and nothing is copied:
+        this is the cheapest way to hand per-step uploaded operators to the layers (12 B/nnz on the host link instead
+        of the reference's 40 B/nnz of int64 COO).  ``to_host_csr()`` produces the matching host arrays."""
+        self = cls.__new__(cls)
+        _require_cuda(rowptr, colidx, vals_xy)
+        if rowptr.dtype != torch.int32 or colidx.dtype != torch.int32 or vals_xy.dtype != torch.float32:
+            raise RuntimeError("from_csr expects int32 rowptr/colidx and float32 values")
+        self.V, self.device = int(V), rowptr.device
+        self.nnz = int(colidx.numel())
+        rowptr, colidx, vals = rowptr.contiguous(), colidx.contiguous(), vals_xy.contiguous().view(-1)
+        if self.nnz == 0:
+            colidx = torch.empty(1, dtype=torch.int32, device=self.device)
+            vals = torch.empty(2, dtype=torch.float32, device=self.device)
+        self.csr = (_lib.dn_csr(rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(), self.nnz), rowptr, colidx, vals)
+        self._coo = None
+        self._csr_t = None
+        return self
+
+    def to_host_csr(self):
+        """(rowptr int32, colidx int32, vals (nnz,2) float32) as pinned host tensors (see ``from_csr``)."""
+        _, rowptr, colidx, vals = self.csr
+        pin = lambda t: t.cpu().contiguous().pin_memory()
+        return pin(rowptr), pin(colidx[:self.nnz]), pin(vals[:2 * self.nnz].view(-1, 2))
+
     def locality(self):
         """Share of entries whose column lies within 8 rows of their row: a proxy for how much of a row's gather the
         neighbouring warps of a CTA (8 consecutive rows) have already pulled into L1.  0.43 on a row-major grid
@@ -209,6 +236,17 @@ class GradOperators:
     @property
     def csr_t(self):
         """CSR of the transposed pattern (backward pass); index sort is prep-time plumbing."""
+        if self._csr_t is None and self._coo is None:      # built by from_csr: transpose on the device
+            _, rowptr, colidx, vals = self.csr
+            rt = torch.empty(self.V + 1, dtype=torch.int32, device=self.device)
+            ct = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=self.device)
+            vt = torch.empty(2 * max(self.nnz, 1), dtype=torch.float32, device=self.device)
+            scratch = torch.empty(max(self.V, 1), dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.load().dn_csr_transpose(C.byref(self.csr[0]), self.V, rt.data_ptr(), ct.data_ptr(),
+                                                        vt.data_ptr(), scratch.data_ptr(), 4 * scratch.numel(),
+                                                        _stream()), "dn_csr_transpose")
+            self._csr_t = (_lib.dn_csr(rt.data_ptr(), ct.data_ptr(), vt.data_ptr(), self.nnz), rt, ct, vt)
         if self._csr_t is None:
             rows, cols, vx, vy = self._coo
             order = torch.argsort(cols * self.V + rows)

@@ -212,7 +212,8 @@ int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const
 
 /* Profiling hook: the same launch sequence as dn_block_fwd with CUDA events recorded on `stream` between its stages;
  * SYNCHRONISES on the last event and writes DN_PROFILE_STAGES host floats (milliseconds):
- *   [0] to_basis (split-V partials)  [1] partial reduction + exp(-lambda t) scale  [2] weight split/pack
+ *   [0] to_basis (split-V partials)  [1] partial reduction + exp(-lambda t) scale when it is a separate launch
+ *   (SIMT engine; 0 on the tensor-core path, where it is part of [2])  [2] weight split/pack (+ reduction and scale)
  *   [3] from_basis (+ [P|Q]) chain   [4] sparse gradient gather + inner product + tanh   [5] MiniMLP chain + skip
  * (bench.py reports each stage's roofline from these).  Not for use inside CUDA-graph capture. */
 #define DN_PROFILE_STAGES 6
