@@ -229,6 +229,205 @@ def measure_tf32_peak(dev, secs=1.0):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+# ------------------------------------------------------------------------------------------------
+# Auxiliary workloads (BASELINE.json configs 2, 4, 5).  The headline metric and the driver's runs use the default
+# `--workload block_fwd`; these print the same kind of JSON line for their own metric.
+# ------------------------------------------------------------------------------------------------
+def _seeded_net(dn, C_in, C_out, C, n_block, dev, seed=0):
+    """4-block DiffusionNet with seeded weights (dropout off: the bench compares numerically identical runs)."""
+    import torch
+    net = dn.DiffusionNet(C_in=C_in, C_out=C_out, C_width=C, N_block=n_block, dropout=False,
+                          last_activation=lambda x: torch.nn.functional.log_softmax(x, dim=-1))
+    g = torch.Generator().manual_seed(77 + seed)
+    sd = net.state_dict()
+    for k, v in sd.items():
+        if k.endswith("diffusion_time"):
+            v.copy_(1e-3 + 0.3 * torch.rand(v.shape, generator=g))
+        else:
+            fan_in = v.shape[-1] if v.dim() > 1 else C
+            v.copy_((torch.rand(v.shape, generator=g) * 2 - 1) / (fan_in ** 0.5))
+    net.load_state_dict(sd)
+    return net.to(dev)
+
+
+def _reference_net(state_dict, C_in, C_out, C, n_block, dev):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_import
+    if not ref_import.reference_available():
+        return None
+    ref = ref_import.import_reference()
+    net = ref.layers.DiffusionNet(C_in=C_in, C_out=C_out, C_width=C, N_block=n_block, dropout=False,
+                                  last_activation=lambda x: torch.nn.functional.log_softmax(x, dim=-1))
+    net.load_state_dict(state_dict, strict=True)
+    return net.to(dev)
+
+
+def _mesh_batch(dn, shapes, K, C_in, dev, seed0=0):
+    import torch
+    out = []
+    for i, (n, m) in enumerate(shapes):
+        ops_t = dn.synthetic.structural_operators(n, m, K, seed=seed0 + i, device=dev)
+        g = torch.Generator().manual_seed(900 + seed0 + i)
+        x = torch.randn(n * m, C_in, generator=g).to(dev)
+        y = torch.randint(0, 8, (n * m,), generator=g).to(dev)
+        out.append((x, y, ops_t))
+    return out
+
+
+def _net_loss(net, x, y, ops_t):
+    import torch
+    mass, L, evals, evecs, gX, gY = ops_t
+    pred = net(x, mass, L=None, evals=evals, evecs=evecs, gradX=gX, gradY=gY)
+    return torch.nn.functional.nll_loss(pred, y)
+
+
+def run_aux(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    import diffusion_net_b200 as dn
+    assert torch.cuda.is_available()
+    dn.dist.bind_to_gpu_numa(local)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    dn.set_engine(args.engine)
+    lib = dn._lib.load()
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    K, C, C_in, C_out, NB = 128, 128, 16, 8, 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(warm):
+            fn()
+        barrier()
+        l0 = lib.dn_kernel_launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, int(lib.dn_kernel_launch_count() - l0)
+
+    line = {"unit": "Mverts/s", "n_gpus": world, "steps": steps, "warmup": warm, "higher_is_better": True,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    if args.workload == "fwd_bwd":
+        # config 2: human-seg shape, one mesh per GPU, forward + backward of the 4-block net (no optimiser)
+        shapes = [(84, 84)]
+        net = _seeded_net(dn, C_in, C_out, C, NB, dev, seed=0).train()
+        (x, y, ops_t), = _mesh_batch(dn, shapes, K, C_in, dev, seed0=rank)
+        V = x.shape[0]
+
+        def step():
+            for p_ in net.parameters():
+                p_.grad = None
+            _net_loss(net, x, y, ops_t).backward()
+        ms, launches = timed(step)
+        with torch.no_grad():
+            net.eval()
+            ms_f, _ = timed(lambda: _net_loss(net, x, y, ops_t))
+            net.train()
+        gpu_base = None
+        if rank == 0 and world == 1:
+            try:
+                prev = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = False
+                rnet = _reference_net(net.state_dict(), C_in, C_out, C, NB, dev)
+                if rnet is not None:
+                    rnet.train()
+
+                    def rstep():
+                        for p_ in rnet.parameters():
+                            p_.grad = None
+                        _net_loss(rnet, x, y, ops_t).backward()
+                    rms, _ = timed(rstep)
+                    # gradient parity of the two arms on the same inputs
+                    step(); rstep()
+                    worst = 0.0
+                    for (n1, p1), (n2, p2) in zip(net.named_parameters(), rnet.named_parameters()):
+                        worst = max(worst, float((p1.grad - p2.grad).abs().max() / (p2.grad.abs().max() + 1e-30)))
+                    gpu_base = {"value": V / (rms * 1e-3) / 1e6, "unit": "Mverts/s", "ms_per_step": rms,
+                                "kind": "reference", "how": "reference DiffusionNet, torch eager autograd on this B200, "
+                                "fp32 (TF32 off)", "speedup_ours": rms / ms, "max_rel_grad_diff_vs_ours": worst}
+                torch.backends.cuda.matmul.allow_tf32 = prev
+            except Exception as exc:
+                gpu_base = {"unavailable": repr(exc)[:200]}
+        line.update({"metric": "DiffusionNet (4 blocks) forward+backward Mverts/sec at V=7056,K=128,C=128",
+                     "value": world * V / (ms * 1e-3) / 1e6, "ms_per_step": ms, "scaling": "weak",
+                     "config": {"workload": "net_fwd_bwd V=7056 K=128 C=128 4 blocks, 1 mesh per GPU",
+                                "engine": args.engine, "forward_only_ms": ms_f},
+                     "gpu_launches": launches, "gpu_baseline": gpu_base})
+    elif args.workload == "train":
+        # config 5: global batch of 8 meshes (V = 20000 each), data parallel: every rank takes 8 / world meshes, one flat
+        # NCCL all-reduce of the gradients (mean over the 8 meshes), one Adam step.  Strong scaling (global work fixed).
+        n_global = 8
+        shards = dn.dist.shard_meshes([dn.dist.mesh_cost(20000, K, C)] * n_global, world)
+        mine = shards[rank]
+        net = _seeded_net(dn, C_in, C_out, C, NB, dev, seed=0).train()
+        meshes = _mesh_batch(dn, [(100, 200)] * n_global, K, C_in, dev, seed0=0)
+        meshes = [meshes[i] for i in mine]
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+        ar_ms = []
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            for x, y, ops_t in meshes:
+                _net_loss(net, x, y, ops_t).backward()         # gradients accumulate over this rank's meshes
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dn.dist.allreduce_gradients(net.parameters(), n_global_meshes=n_global)
+            e1.record()
+            ar_ms.append((e0, e1))
+            opt.step()
+        ms, launches = timed(step)
+        torch.cuda.synchronize()
+        ar = sorted(a.elapsed_time(b) for a, b in ar_ms[-steps:])
+        Vtot = n_global * 20000
+        nparam = sum(p_.numel() for p_ in net.parameters())
+        line.update({"metric": "DiffusionNet (4 blocks) data-parallel training step, 8 meshes V=20000, Mverts/sec",
+                     "value": Vtot / (ms * 1e-3) / 1e6, "ms_per_step": ms, "scaling": "strong",
+                     "config": {"workload": "train 8 meshes V=20000 K=128 C=128 4 blocks, dp{}".format(world),
+                                "engine": args.engine, "meshes_per_rank": len(mine), "optimizer": "Adam",
+                                "allreduce": "one flat fp32 buffer of {} floats, NCCL".format(nparam),
+                                "allreduce_ms_median": ar[len(ar) // 2], "allreduce_ms_max": ar[-1]},
+                     "gpu_launches": launches})
+    else:
+        # config 4: 32 small meshes (V ~ 2k), 4-block net forward, meshes sharded over the ranks, CUDA-graph replay
+        n_global = 32
+        shapes = [(36 + i % 9, 50) for i in range(n_global)]
+        shards = dn.dist.shard_meshes([dn.dist.mesh_cost(a * b, K, C) for a, b in shapes], world)
+        mine = shards[rank]
+        net = _seeded_net(dn, C_in, C_out, C, NB, dev, seed=0).eval()
+        meshes = _mesh_batch(dn, shapes, K, C_in, dev, seed0=0)
+        items = [dict(x_in=meshes[i][0], mass=meshes[i][2][0], evals=meshes[i][2][2], evecs=meshes[i][2][3],
+                      gradX=meshes[i][2][4], gradY=meshes[i][2][5]) for i in mine]
+        gn = dn.graphs.GraphedNet(net, n_streams=4)
+        with torch.no_grad():
+            ms, launches = timed(lambda: gn.forward_batch(items))
+        Vtot = sum(a * b for a, b in shapes)
+        line.update({"metric": "DiffusionNet (4 blocks) forward over a batch of 32 small meshes, Mverts/sec",
+                     "value": Vtot / (ms * 1e-3) / 1e6, "ms_per_step": ms, "scaling": "strong",
+                     "config": {"workload": "small_batch 32 meshes V~2k K=128 C=128 4 blocks, sharded x{}".format(world),
+                                "engine": args.engine, "meshes_per_rank": len(mine), "replay": "CUDA graphs, 4 streams"},
+                     "gpu_launches": launches})
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -238,6 +437,8 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("DN_B200_ENGINE", "tc3x"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--workload", default="block_fwd", choices=["block_fwd", "fwd_bwd", "train", "small_batch"],
+                    help="block_fwd = the BASELINE metric (default); the others are BASELINE configs 2 / 5 / 4")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,6 +446,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload != "block_fwd":
+        run_aux(args, rank, world, local)
         return
 
     import torch

@@ -83,6 +83,28 @@ int to_basis_partials(const float* values, const float* basis, const float* mass
   return simt_atb_partial_st(basis, K, K, values, C, C, massvec, V, partial, partial_floats, P, st);
 }
 
+// out[i][j] (ld_out) (+)= sum_v A[v][i] * B[v][j]   (weight gradients: A = dz, B = layer input).
+// Tensor cores (the split-V to_basis kernel, reference geometry.py:572-583 has the same contraction) when both
+// operands are contiguous and at most 128 wide; the exact SIMT kernel otherwise.
+int atb(const float* A, int64_t lda, int I, const float* B, int64_t ldb, int J, int64_t V, float* out, int64_t ld_out,
+        int accumulate, float* part, int64_t part_floats, int engine, cudaStream_t st) {
+  if (use_tc(engine) && tc_supported_device() && lda == I && ldb == J && tc_to_basis_supported(I, J) == DN_OK &&
+      (int64_t)148 * I * J <= part_floats) {
+    int P = 0;
+    int rc = tc_to_basis_partial(B, A, nullptr, V, I, J, part, &P, tc_passes(engine), st);
+    if (rc == DN_OK) return launch_reduce_partials_ld(part, P, I, J, out, ld_out, accumulate, st);
+    if (rc != DN_ERR_UNSUPPORTED) return rc;
+  }
+  return simt_atb(A, lda, I, B, ldb, J, nullptr, V, out, ld_out, accumulate, part, part_floats, st);
+}
+
+// one dense layer on the tensor-core chain kernel when it takes the shape, else the exact SIMT kernel
+int one_layer(const DnRowsSrc& src, DnLayer& L, int64_t V, int engine, void* tc_ws, int64_t tc_ws_bytes, cudaStream_t st) {
+  if (use_tc(engine) && tc_supported_device() && tc_rows_chain_supported(src, &L, 1) == DN_OK)
+    return tc_rows_chain(src, &L, 1, V, tc_passes(engine), tc_ws, tc_ws_bytes, st);
+  return simt_rows_gemm(src, L, V, st);
+}
+
 }  // namespace
 
 long long g_dn_launches = 0;
@@ -355,39 +377,48 @@ int dn_gradient_features_bwd(const dn_csr* grad, const dn_csr* grad_t, const flo
       (with_gradient_rotations && (!A_im || !grad_A_im)))
     return DN_ERR_INVALID_ARGUMENT;
   if (C % 4) return DN_ERR_UNSUPPORTED;
-  (void)engine;
   cudaStream_t st = (cudaStream_t)stream;
   Bump ws(workspace, ws_bytes);
-  const int npq = with_gradient_rotations ? 2 * C : C;
+  const int rot = with_gradient_rotations;
   float* U = ws.take(V * 4 * C);
   float* dxd = ws.take(V * C);
-  float* dpq = ws.take(V * npq);
+  float* dP = ws.take(V * C);                      // dP, dQ as two contiguous (V, C) matrices: they are the chain
+  float* dQ = rot ? ws.take(V * C) : nullptr;      // kernel's two sources and the weight-gradient kernel's operands
   float* part = ws.take(kPartialFloats / 4);
-  if (!U || !dxd || !dpq || !part) return DN_ERR_WORKSPACE;
+  if (!U || !dxd || !dP || (rot && !dQ) || !part) return DN_ERR_WORKSPACE;
+  void* tcws = ws.base + ws.off;
+  const int64_t tcws_bytes = ws.size - ws.off;
   int rc;
-  if ((rc = launch_features_bwd_local(grad, x_diffuse, pq, features, grad_features, with_gradient_rotations, V, C,
-                                      U, st)))
-    return rc;
-  if ((rc = launch_features_bwd_transpose(grad_t, U, with_gradient_rotations, V, C, dxd, dpq, st))) return rc;
-  // grad_x = dxd + dP A_re (+ dQ A_im)
+  if ((rc = launch_features_bwd_local(grad, x_diffuse, pq, features, grad_features, rot, V, C, U, st))) return rc;
+  if ((rc = launch_features_bwd_transpose(grad_t, U, rot, V, C, dxd, dP, dQ, C, st))) return rc;
+  // grad_x = dxd + dP A_re (+ dQ A_im): one layer over the sources (dP | dQ) with [A_re ; A_im] stacked along K
   {
-    DnRowsSrc s = one_src(dpq, C, npq);
-    DnLayer L = make_layer(A_re, C, /*w_trans=*/1, nullptr, 0, C, C, grad_x, C);
+    DnRowsSrc s;
+    memset(&s, 0, sizeof(s));
+    s.ptr[0] = dP; s.width[0] = C; s.ld[0] = C; s.nsrc = 1;
+    if (rot) { s.ptr[1] = dQ; s.width[1] = C; s.ld[1] = C; s.nsrc = 2; }
+    DnLayer L = make_layer(A_re, C, /*w_trans=*/1, nullptr, 0, rot ? 2 * C : C, C, grad_x, C);
+    if (rot) { L.W2 = A_im; L.n_split = C; }
     L.residual = dxd; L.ld_res = C;
-    if ((rc = simt_rows_gemm(s, L, V, st))) return rc;
-    if (with_gradient_rotations) {
-      DnRowsSrc s2 = one_src(dpq + C, C, npq);
-      DnLayer M = make_layer(A_im, C, 1, nullptr, 0, C, C, grad_x, C);
-      M.residual = grad_x; M.ld_res = C;
-      if ((rc = simt_rows_gemm(s2, M, V, st))) return rc;
+    if (use_tc(engine) && tc_supported_device() && tc_rows_chain_supported(s, &L, 1) == DN_OK) {
+      if ((rc = tc_rows_chain(s, &L, 1, V, tc_passes(engine), tcws, tcws_bytes, st))) return rc;
+    } else {                                       // exact SIMT route: one source at a time
+      DnRowsSrc s0 = one_src(dP, C, C);
+      DnLayer L0 = make_layer(A_re, C, 1, nullptr, 0, C, C, grad_x, C);
+      L0.residual = dxd; L0.ld_res = C;
+      if ((rc = simt_rows_gemm(s0, L0, V, st))) return rc;
+      if (rot) {
+        DnRowsSrc s1 = one_src(dQ, C, C);
+        DnLayer L1 = make_layer(A_im, C, 1, nullptr, 0, C, C, grad_x, C);
+        L1.residual = grad_x; L1.ld_res = C;
+        if ((rc = simt_rows_gemm(s1, L1, V, st))) return rc;
+      }
     }
   }
-  // grad_A_re[n][k] += sum_v dP[v][n] xd[v][k]
-  if ((rc = simt_atb(dpq, npq, C, x_diffuse, C, C, nullptr, V, grad_A_re, C, 1, part, kPartialFloats / 4, st)))
-    return rc;
-  if (with_gradient_rotations)
-    if ((rc = simt_atb(dpq + C, npq, C, x_diffuse, C, C, nullptr, V, grad_A_im, C, 1, part, kPartialFloats / 4, st)))
-      return rc;
+  // grad_A_re[n][k] += sum_v dP[v][n] xd[v][k]   (and grad_A_im from dQ)
+  if ((rc = atb(dP, C, C, x_diffuse, C, C, V, grad_A_re, C, 1, part, kPartialFloats / 4, engine, st))) return rc;
+  if (rot)
+    if ((rc = atb(dQ, C, C, x_diffuse, C, C, V, grad_A_im, C, 1, part, kPartialFloats / 4, engine, st))) return rc;
   return DN_OK;
 }
 
@@ -442,7 +473,6 @@ int dn_mini_mlp_bwd(const float* grad_out, const float* const* src_host, const i
       n_layers < 1 || n_layers > DN_MAX_LAYERS || (n_layers > 1 && !hidden_host) || !grad_src_host ||
       !grad_weight_host)
     return DN_ERR_INVALID_ARGUMENT;
-  (void)engine;
   cudaStream_t st = (cudaStream_t)stream;
   int maxn = 0;
   for (int l = 0; l <= n_layers; ++l) maxn = dims_host[l] > maxn ? dims_host[l] : maxn;
@@ -451,34 +481,36 @@ int dn_mini_mlp_bwd(const float* grad_out, const float* const* src_host, const i
   float* d1 = ws.take(V * maxn);
   float* part = ws.take(kPartialFloats / 2);
   if (!d0 || !d1 || !part) return DN_ERR_WORKSPACE;
+  void* tcws = ws.base + ws.off;
+  const int64_t tcws_bytes = ws.size - ws.off;
   const float* dz = grad_out;   // gradient w.r.t. the pre-activation of layer l
   int rc;
   for (int l = n_layers - 1; l >= 0; --l) {
     const int nout = dims_host[l + 1], nin = dims_host[l];
-    // weight / bias gradients
+    // weight / bias gradients:  grad_W[n][k] += sum_v dz[v][n] * h_{l-1}[v][k]
     if (l > 0) {
-      if ((rc = simt_atb(dz, nout, nout, hidden_host[l - 1], nin, nin, nullptr, V, grad_weight_host[l], nin, 1, part,
-                         kPartialFloats / 2, st)))
+      if ((rc = atb(dz, nout, nout, hidden_host[l - 1], nin, nin, V, grad_weight_host[l], nin, 1, part,
+                    kPartialFloats / 2, engine, st)))
         return rc;
     } else {
       int off = 0;
       for (int s = 0; s < nsrc; ++s) {
-        if ((rc = simt_atb(dz, nout, nout, src_host[s], src_width_host[s], src_width_host[s], nullptr, V,
-                           grad_weight_host[0] + off, nin, 1, part, kPartialFloats / 2, st)))
+        if ((rc = atb(dz, nout, nout, src_host[s], src_width_host[s], src_width_host[s], V, grad_weight_host[0] + off,
+                      nin, 1, part, kPartialFloats / 2, engine, st)))
           return rc;
         off += src_width_host[s];
       }
     }
     if (grad_bias_host && grad_bias_host[l])
       if ((rc = simt_colsum(dz, nout, nout, V, grad_bias_host[l], 1, st))) return rc;
-    // input gradient
+    // input gradient:  dz_{l-1} = (dz_l W_l) * 1[h_{l-1} > 0] (* dropout mask)
     DnRowsSrc s = one_src(dz, nout, nout);
     if (l > 0) {
       float* o = (dz == d0) ? d1 : d0;
       DnLayer L = make_layer(weight_host[l], nin, /*w_trans=*/1, nullptr, 0, nout, nin, o, nin);
       L.relu_mask_src = hidden_host[l - 1];
       if (drop_mask_host && drop_mask_host[l - 1]) L.emul = drop_mask_host[l - 1];
-      if ((rc = simt_rows_gemm(s, L, V, st))) return rc;
+      if ((rc = one_layer(s, L, V, engine, tcws, tcws_bytes, st))) return rc;
       dz = o;
     } else {
       int off = 0;
@@ -486,7 +518,7 @@ int dn_mini_mlp_bwd(const float* grad_out, const float* const* src_host, const i
         if (grad_src_host[q]) {
           DnLayer L = make_layer(weight_host[0] + off, nin, 1, nullptr, 0, nout, src_width_host[q], grad_src_host[q],
                                  src_width_host[q]);
-          if ((rc = simt_rows_gemm(s, L, V, st))) return rc;
+          if ((rc = one_layer(s, L, V, engine, tcws, tcws_bytes, st))) return rc;
         }
         off += src_width_host[q];
       }

@@ -52,16 +52,16 @@ constexpr int C3_IO_BUFS = 6;
 constexpr int C3_WBYTES = 131072;               // weight ring
 constexpr int C3_OFF_W = C3_IO_BUFS * C3_RAW;
 constexpr int C3_OFF_BAR = C3_OFF_W + C3_WBYTES;
-constexpr int C3_BIAS_FLOATS = 512;             // biases of all layers, staged once (sum of N over the layers that have one)
-constexpr int C3_SMEM = C3_OFF_BAR + 512 /*barriers*/ + C3_BIAS_FLOATS * 4;
+constexpr int C3_SMEM = C3_OFF_BAR + 512 /*barriers*/;
 
 struct C3Layer {
   const float* wpack;      // tc_pack_layers layout (16-wide chunks of [hi | lo] images)
   const float* bias;       // [N] or null
   const float* row_scale;  // [V] or null (last layer only)
   int K, N, relu;
-  int has_out, has_res;
-};
+  int has_out;
+  int has_res;             // 0: none | 1: + residual (layers.py:239) | 2: * (aux > 0): backward of ReLU, aux = the
+};                         //    forward activation (last layer only; the tensor is fetched through maps.res)
 
 struct C3Params {
   C3Layer layer[DN_MAX_LAYERS];
@@ -71,7 +71,6 @@ struct C3Params {
   int ring_col;    // first TMEM column of the operand ring
   int ns_shift;    // log2(ring depth): 2 -> 4 stages (32 KiB weight slots), 1 -> 2 stages (64 KiB weight slots)
   int nr_shift;    // log2(row-box slots): 2 or 1;  output staging buffers = 6 - slots
-  int bias_smem;   // biases fit the staging area (else the epilogues read them with __ldg)
   int64_t V;
   long long* trace;   // optional (tools/trace_chain3.py): per-warp (event, clock64) pairs of CTA 0
 };
@@ -148,7 +147,7 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
   const uint32_t nout = (uint32_t)C3_IO_BUFS - (1u << nr_sh), nout_mask = nout - 1u;   // 2 or 4
   const uint32_t raw_u = smem0, out_u = smem0 + ((uint32_t)C3_RAW << nr_sh), w_u = smem0 + C3_OFF_W;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C3_OFF_BAR);
-  float* sbias = reinterpret_cast<float*>(smem + C3_OFF_BAR + 512);
+
   // bars: raw_full[4] raw_empty[4] full[4] ab_empty[4] dm_full[2] do_full[2] dm_empty[2] do_empty[2] res[4 warps][2] done
   //   full[s]     : operand stage s AND weight stage s are ready (4 operand-warp arrivals + the weight producer's
   //                 arrive.expect_tx): the MMA warp waits once per stage
@@ -182,15 +181,6 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
   if (warp == 3) tmem_alloc<512>(smem_u32(tmem_slot));
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.nsrc; ++s) prefetch_tmap(&maps.src[s]);
-  }
-  if (p.bias_smem) {                       // layer l's bias at sbias[sum of N over earlier layers]
-    int off = 0;
-    for (int l = 0; l < p.n_layers; ++l) {
-      const int N = p.layer[l].N;
-      if (p.layer[l].bias)
-        for (int i = threadIdx.x; i < N; i += blockDim.x) sbias[off + i] = __ldg(p.layer[l].bias + i);
-      off += N;
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -270,16 +260,12 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         }
         tc_fence_after();
         C3_TRACE(24);
-        uint32_t ready = 0;                                   // this stage's barrier was already seen complete
         for (int c = 0; c < nst; ++c, ++i) {
           const uint32_t s = i & ns_mask, ph = (i >> ns_sh) & 1u;
           C3_TRACE(20);
-          if (!ready) mbar_wait(full + 8 * s, ph);
+          mbar_wait(full + 8 * s, ph);
           C3_TRACE(21);
           tc_fence_after();
-          // probe the next stage while this one is issued: a completed barrier then costs nothing on the way round
-          ready = (c + 1 < nst) ? mbar_test(full + 8 * ((i + 1) & ns_mask), ((i + 1) >> ns_sh) & 1u) : 0u;
-          ready = __all_sync(0xffffffffu, ready != 0) ? 1u : 0u;     // every lane observed it (acquire per lane)
           if (elect_one()) {
             const uint32_t a0 = tmem_base + (uint32_t)p.ring_col + s * 64u;
             const uint64_t dbs = tmplB + (w_u4 + s * (w_slot >> 4));
@@ -347,7 +333,6 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
     uint32_t um0 = 0, um1 = 0;                          // chained-epilogue uses of accumulator buffer 0 / 1 so far
     int S = 0;
     for (int l = 0; l < L; ++l) S += p.layer[l].K / C3_KS;
-    const bool bsm = p.bias_smem != 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_seq) {
       const uint32_t i_base = t_seq * (uint32_t)S, r_base = t_seq * (uint32_t)nst0;
       // ---- layer 0: my stages of the row boxes -> TMEM
@@ -378,6 +363,13 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         const uint32_t g = t_seq * (uint32_t)L + (uint32_t)l;
         const uint32_t buf = two ? (g & 1u) : 0u;
         const int nco = Lr.N / C3_KS;
+        // this warpgroup's chunks are c = wg, wg + 2, ... (at most 4 at N = 256): their bias lanes, in flight during the wait
+        float bl[4] = {0.f, 0.f, 0.f, 0.f};
+        if (Lr.bias) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if ((int)wg + 2 * q < nco) bl[q] = __ldg(Lr.bias + ((int)wg + 2 * q) * C3_KS + lane);
+        }
         C3_TRACE(10);
         mbar_wait(dm_full + 8 * buf, (buf ? um1 : um0) & 1u);
         C3_TRACE(11);
@@ -385,8 +377,6 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         tc_fence_after();
         const uint32_t d_lane = lane_base + buf * 128u;
         bool released = false;
-        int boff = 0;
-        for (int q = 0; q < l; ++q) boff += p.layer[q].N;
         for (int c = (int)wg; c < nco; c += 2) {
           float v[32];
           tmem_ld32(d_lane + (uint32_t)c * C3_KS, v);
@@ -398,13 +388,10 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
             released = true;
           }
           if (Lr.bias) {
-            const float4* bp = bsm ? reinterpret_cast<const float4*>(sbias + boff + c * C3_KS)
-                                   : reinterpret_cast<const float4*>(Lr.bias + c * C3_KS);
+            const int qi = (c - (int)wg) >> 1;
+            const float mine = qi == 0 ? bl[0] : (qi == 1 ? bl[1] : (qi == 2 ? bl[2] : bl[3]));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = bp[j];                      // (broadcast LDS when staged)
-              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
+            for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, mine, j);
           }
           if (Lr.relu) {
 #pragma unroll
@@ -429,7 +416,6 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
     const uint32_t my_res = res_bar + 8u * (uint32_t)(quarter * 4);
     uint32_t oc = 0;                 // output chunks issued so far (staging buffer = oc mod nout)
     uint32_t rcbits = 0;             // bit b: parity of the residual loads waited so far on staging buffer b
-    const bool bsm = p.bias_smem != 0;
     uint32_t uo0 = 0, uo1 = 0;       // output uses of accumulator buffer 0 / 1 so far
     uint32_t t_seq = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_seq) {
@@ -446,8 +432,12 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         const bool res = Lr.has_res != 0;
         const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
         const uint32_t d_lane = lane_base + buf * 128u;
-        int boff = 0;
-        for (int q = 0; q < l; ++q) boff += p.layer[q].N;
+        float bl[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // bias lane of each chunk (N <= 256)
+        if (Lr.bias) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < nco) bl[q] = __ldg(Lr.bias + q * C3_KS + lane);
+        }
         C3_TRACE(30);
         if (!res) {
           mbar_wait(do_full + 8 * buf, use & 1u);
@@ -494,13 +484,11 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
               if (lane == 0) mbar_arrive(do_empty + 8 * buf);
             }
             if (Lr.bias) {
-              const float4* bp = bsm ? reinterpret_cast<const float4*>(sbias + boff + c * C3_KS)
-                                     : reinterpret_cast<const float4*>(Lr.bias + c * C3_KS);
+              float mine = bl[0];
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const float4 bb = bp[jj];
-                v[4 * jj] += bb.x; v[4 * jj + 1] += bb.y; v[4 * jj + 2] += bb.z; v[4 * jj + 3] += bb.w;
-              }
+              for (int q = 1; q < 8; ++q) mine = (c == q) ? bl[q] : mine;
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) v[jj] += __shfl_sync(0xffffffffu, mine, jj);
             }
             if (Lr.relu) {
 #pragma unroll
@@ -515,10 +503,19 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
               mbar_wait(my_res + 8 * b, (rcbits >> b) & 1u);
               C3_TRACE(34);
               rcbits ^= (1u << b);
+              if (Lr.has_res == 1) {
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const float4 q = lds128(rowaddr + ((((uint32_t)jj) ^ swz) << 4));
-                v[4 * jj] += q.x; v[4 * jj + 1] += q.y; v[4 * jj + 2] += q.z; v[4 * jj + 3] += q.w;
+                for (int jj = 0; jj < 8; ++jj) {
+                  const float4 q = lds128(rowaddr + ((((uint32_t)jj) ^ swz) << 4));
+                  v[4 * jj] += q.x; v[4 * jj + 1] += q.y; v[4 * jj + 2] += q.z; v[4 * jj + 3] += q.w;
+                }
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const float4 q = lds128(rowaddr + ((((uint32_t)jj) ^ swz) << 4));
+                  v[4 * jj] = q.x > 0.f ? v[4 * jj] : 0.f;         v[4 * jj + 1] = q.y > 0.f ? v[4 * jj + 1] : 0.f;
+                  v[4 * jj + 2] = q.z > 0.f ? v[4 * jj + 2] : 0.f; v[4 * jj + 3] = q.w > 0.f ? v[4 * jj + 3] : 0.f;
+                }
               }
             }
 #pragma unroll
@@ -606,8 +603,9 @@ int tc_chain3_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layer
     const DnLayer& L = layers[l];
     const bool last = (l + 1 == n_layers);
     if (L.K % 64 || L.K < 64 || L.N % C3_KS || L.N < C3_KS || L.N > 256) return DN_ERR_UNSUPPORTED;
-    if (L.emul || L.relu_mask_src) return DN_ERR_UNSUPPORTED;
-    if (L.W2 && L.w_trans) return DN_ERR_UNSUPPORTED;
+    if (L.emul) return DN_ERR_UNSUPPORTED;
+    if (L.relu_mask_src && (!last || L.residual || (reinterpret_cast<uintptr_t>(L.relu_mask_src) & 15)))
+      return DN_ERR_UNSUPPORTED;
     if (L.bias && (reinterpret_cast<uintptr_t>(L.bias) & 15)) return DN_ERR_UNSUPPORTED;
     if (!last && (L.residual || L.row_scale)) return DN_ERR_UNSUPPORTED;
     if (!last && L.N % 64) return DN_ERR_UNSUPPORTED;             // it is the next layer's K
@@ -656,28 +654,27 @@ int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, in
     C3Layer& T = p.layer[l];
     if (!L.prepacked) return DN_ERR_INVALID_ARGUMENT;
     T.wpack = L.prepacked; T.bias = L.bias; T.row_scale = L.row_scale; T.K = L.K; T.N = L.N; T.relu = L.relu;
-    T.has_out = L.out != nullptr; T.has_res = L.residual != nullptr;
+    T.has_out = L.out != nullptr;
+    T.has_res = L.residual ? 1 : (L.relu_mask_src ? 2 : 0);
     if (L.out && make_box_map(&maps.out[l], L.out, L.N, L.ld_out, V, 32)) return DN_ERR_UNSUPPORTED;
     if (L.residual && make_box_map(&maps.res, L.residual, L.N, L.ld_res, V, 32)) return DN_ERR_UNSUPPORTED;
+    if (L.relu_mask_src && make_box_map(&maps.res, L.relu_mask_src, L.N, L.N, V, 32)) return DN_ERR_UNSUPPORTED;
     if (L.N > nmax) nmax = L.N;
   }
   if (nmax <= 128) { p.nbuf = 2; p.ring_col = 256; p.ns_shift = 2; }
   else if (n_layers == 2) { p.nbuf = 2; p.ring_col = 384; p.ns_shift = 1; }
   else { p.nbuf = 1; p.ring_col = 256; p.ns_shift = 1; }
   // output-heavy chains (few layer-0 stages per tile, many output columns): 2 row-box slots + 4 staging buffers
-  int out_cols = 0, bias_floats = 0;
-  for (int l = 0; l < n_layers; ++l) {
-    if (layers[l].out) out_cols += layers[l].N;
-    bias_floats += layers[l].N;
-  }
-  p.nr_shift = (out_cols > layers[0].K) ? 1 : 2;
+  // (measured on the from_basis -> [P|Q] chain: 2 + 4 was SLOWER, 124 vs 108 us -- the extra staging traffic competes
+  //  with the tensor core for shared-memory bandwidth -- so 4 + 2 stays the default; DN_C3_NR=2 selects 2 + 4)
+  p.nr_shift = 2;
   {
     static int nr_env = -2;
     if (nr_env == -2) { const char* e = getenv("DN_C3_NR"); nr_env = e ? atoi(e) : -1; }
     if (nr_env == 2) p.nr_shift = 1;
     if (nr_env == 4) p.nr_shift = 2;
   }
-  p.bias_smem = bias_floats <= C3_BIAS_FLOATS ? 1 : 0;
+
   const int64_t ntiles = (V + C3_TILE - 1) / C3_TILE;
   const int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
   rows_chain3_kernel<<<grid, C3_THREADS, C3_SMEM, st>>>(p, maps);

@@ -30,8 +30,8 @@ struct DnLayer {
   const float* W;        // nn.Linear layout [N][K] (ldw = K) when !w_trans; [K][N] (ldw = N) when w_trans
   int64_t ldw;
   int w_trans;
-  const float* W2;       // optional second block of output rows (!w_trans only): rows n >= n_split
-  int n_split;           //   come from W2[n - n_split]  (stacks [A_re; A_im] without a copy)
+  const float* W2;       // optional second block: !w_trans: output rows n >= n_split come from W2[n - n_split]
+  int n_split;           //   (stacks [A_re; A_im] without a copy);  w_trans: input rows k >= n_split come from W2[k - n_split]
   const float* prepacked;  // optional: weights already in the tensor-core layout (tc_pack_layers)
   const float* bias;     // [N] or null
   int relu;
@@ -69,6 +69,8 @@ int simt_colsum(const float* A, int64_t lda, int N, int64_t V, float* out, int a
 int launch_spectral_scale(const float* partial, int P, const float* evals, float* time, int K, int C,
                           float* x_spec_out, float* S_out, int clamp_writeback, cudaStream_t st);
 int launch_reduce_partials(const float* partial, int P, int64_t n, float* out, cudaStream_t st);
+int launch_reduce_partials_ld(const float* partial, int P, int rows, int cols, float* out, int64_t ld_out,
+                              int accumulate, cudaStream_t st);
 int launch_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* vx, const float* vy,
                         int64_t nnz, int64_t V, int32_t* rowptr, int32_t* colidx, float* vals, cudaStream_t st);
 int launch_compute_hks(const float* evals, const float* evecs, const float* scales, int64_t V, int K, int S,
@@ -83,7 +85,8 @@ int launch_features_bwd_local(const dn_csr* g, const float* xd, const float* pq,
                               const float* dfeat, int rotations, int64_t V, int C, float* U /*V x 4C*/,
                               cudaStream_t st);
 int launch_features_bwd_transpose(const dn_csr* gt, const float* U, int rotations, int64_t V, int C,
-                                  float* dxd /*V x C*/, float* dpq /*V x 2C*/, cudaStream_t st);
+                                  float* dxd /*V x C*/, float* dP, float* dQ /*V x C each, leading dim ld_pq*/,
+                                  int64_t ld_pq, cudaStream_t st);
 int launch_deinterleave_vc2(const float* vc2, int64_t V, int C, float* g01 /*V x 2C*/, cudaStream_t st);
 int launch_complex_dots_tanh(const float* g01, const float* b01, int64_t V, int C, float* out, cudaStream_t st);
 int launch_spectral_bwd(const float* gs_partial, int P, const float* evals, const float* time,

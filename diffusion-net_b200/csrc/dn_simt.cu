@@ -869,14 +869,14 @@ __global__ void __launch_bounds__(256) features_bwd_local_kernel(
 template <bool ROT>
 __global__ void __launch_bounds__(256) features_bwd_transpose_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const float2* __restrict__ vals,
-    const float* __restrict__ U, int64_t V, int C, int G, float* __restrict__ dxd, float* __restrict__ dpq) {
+    const float* __restrict__ U, int64_t V, int C, int G, float* __restrict__ dxd, float* __restrict__ dP,
+    float* __restrict__ dQ, int64_t ld_pq) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t row = warp * (32 / G) + lane / G;
   const int gl = lane % G;
   if (row >= V) return;
   const int s = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
-  const int ld_pq = ROT ? 2 * C : C;
   for (int c4 = gl; c4 < (C >> 2); c4 += G) {
     float4 ax = make_float4(0.f, 0.f, 0.f, 0.f), ap = ax, aq = ax;
     for (int p = s; p < e; ++p) {
@@ -894,8 +894,8 @@ __global__ void __launch_bounds__(256) features_bwd_transpose_kernel(
       }
     }
     *reinterpret_cast<float4*>(dxd + row * C + c4 * 4) = ax;
-    *reinterpret_cast<float4*>(dpq + row * ld_pq + c4 * 4) = ap;
-    if (ROT) *reinterpret_cast<float4*>(dpq + row * ld_pq + C + c4 * 4) = aq;
+    *reinterpret_cast<float4*>(dP + row * ld_pq + c4 * 4) = ap;
+    if (ROT) *reinterpret_cast<float4*>(dQ + row * ld_pq + c4 * 4) = aq;
   }
 }
 
@@ -1006,6 +1006,14 @@ int launch_reduce_partials(const float* partial, int P, int64_t n, float* out, c
   return DN_OK;
 }
 
+int launch_reduce_partials_ld(const float* partial, int P, int rows, int cols, float* out, int64_t ld_out,
+                              int accumulate, cudaStream_t st) {
+  reduce_partials_ld_kernel<<<(unsigned)((rows * cols + 255) / 256), 256, 0, st>>>(partial, P, rows, cols, out, ld_out,
+                                                                                   accumulate);
+  DN_LAUNCH_CHECK();
+  return DN_OK;
+}
+
 int launch_spectral_bwd(const float* gs_partial, int P, const float* evals, const float* time, const float* x_spec,
                         int K, int C, float* dS, float* grad_time, cudaStream_t st) {
   spectral_bwd_kernel<<<(C + 63) / 64, 64, 0, st>>>(gs_partial, P, evals, time, x_spec, K, C, dS, grad_time);
@@ -1092,7 +1100,7 @@ int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int 
   static int use_pipe = -1;
   if (use_pipe < 0) {
     const char* e = getenv("DN_SPMM_PIPE");
-    use_pipe = e ? atoi(e) : 1;
+    use_pipe = e ? atoi(e) : 0;   // measured (tools/ab_gather.py): 243-261 us vs 181 us for the warp-per-row kernel: opt-in until understood
   }
   if (C == 128 && use_pipe) {
     int dev = 0, nsm = 148;
@@ -1164,7 +1172,7 @@ int launch_features_bwd_local(const dn_csr* g, const float* xd, const float* pq,
 }
 
 int launch_features_bwd_transpose(const dn_csr* gt, const float* U, int rotations, int64_t V, int C, float* dxd,
-                                  float* dpq, cudaStream_t st) {
+                                  float* dP, float* dQ, int64_t ld_pq, cudaStream_t st) {
   if (V <= 0) return DN_OK;
   if (C % 4) return DN_ERR_UNSUPPORTED;
   const int G = pick_group(C);
@@ -1172,9 +1180,9 @@ int launch_features_bwd_transpose(const dn_csr* gt, const float* U, int rotation
   const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
   const float2* vals = reinterpret_cast<const float2*>(gt->vals);
   if (rotations)
-    features_bwd_transpose_kernel<true><<<blocks, 256, 0, st>>>(gt->rowptr, gt->colidx, vals, U, V, C, G, dxd, dpq);
+    features_bwd_transpose_kernel<true><<<blocks, 256, 0, st>>>(gt->rowptr, gt->colidx, vals, U, V, C, G, dxd, dP, dQ, ld_pq);
   else
-    features_bwd_transpose_kernel<false><<<blocks, 256, 0, st>>>(gt->rowptr, gt->colidx, vals, U, V, C, G, dxd, dpq);
+    features_bwd_transpose_kernel<false><<<blocks, 256, 0, st>>>(gt->rowptr, gt->colidx, vals, U, V, C, G, dxd, dP, dQ, ld_pq);
   DN_LAUNCH_CHECK();
   return DN_OK;
 }

@@ -87,25 +87,34 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackJobs jobs) {
   for (int i = 1; i < DN_MAX_LAYERS; ++i)
     if (i < jobs.n && (int)blockIdx.x >= jobs.j[i].blk0) ji = i;
   const PackJob& J = jobs.j[ji];
-  const int idx = ((int)blockIdx.x - J.blk0) * blockDim.x + threadIdx.x;
-  if (idx >= J.K * J.N) return;
   const int K = J.K, N = J.N, kc = jobs.kc;
   int n, k;
   float w;
   if (ji == 0 && jobs.sp_partial) {
-    k = idx / N; n = idx % N;                               // n fastest: coalesced reads of the partial sums
-    float acc0 = 0.f, acc1 = 0.f;
-    const float* pp = jobs.sp_partial + idx;
-    const int64_t stride = (int64_t)K * N;
-    int q = 0;
-    for (; q + 1 < jobs.sp_P; q += 2) { acc0 += pp[(int64_t)q * stride]; acc1 += pp[(int64_t)(q + 1) * stride]; }
-    if (q < jobs.sp_P) acc0 += pp[(int64_t)q * stride];
+    // spectral job: a block = 32 consecutive elements (n fastest: coalesced) x 8 slices of the P partial sums, so the
+    // ~10 MB of partials are read with many loads in flight (one thread per element was 19 us at K = C = 128)
+    __shared__ float red[8][33];
+    const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int idx = ((int)blockIdx.x - J.blk0) * 32 + e;
+    float acc = 0.f;
+    if (idx < K * N) {
+      const float* pp = jobs.sp_partial + idx;
+      const int64_t stride = (int64_t)K * N;
+      for (int q = sl; q < jobs.sp_P; q += 8) acc += pp[(int64_t)q * stride];
+    }
+    red[sl][e] = acc;
+    __syncthreads();
+    if (sl != 0 || idx >= K * N) return;
+    k = idx / N; n = idx % N;
+    const float sum = ((red[0][e] + red[1][e]) + (red[2][e] + red[3][e])) + ((red[4][e] + red[5][e]) + (red[6][e] + red[7][e]));
     const float t = fmaxf(jobs.sp_time[n], 1e-8f);         // torch.clamp(t, min=1e-8)
-    w = expf(-(jobs.sp_evals[k] * t)) * (acc0 + acc1);
+    w = expf(-(jobs.sp_evals[k] * t)) * sum;
     if (jobs.sp_clamp && k == K - 1) jobs.sp_time[n] = t;   // (idempotent for the other readers of t[n])
   } else {
+    const int idx = ((int)blockIdx.x - J.blk0) * blockDim.x + threadIdx.x;
+    if (idx >= K * N) return;
     n = idx / K; k = idx % K;
-    if (J.w_trans) w = J.W[(int64_t)k * J.ldw + n];
+    if (J.w_trans) w = (J.W2 && k >= J.n_split) ? J.W2[(int64_t)(k - J.n_split) * J.ldw + n] : J.W[(int64_t)k * J.ldw + n];
     else if (J.W2 && n >= J.n_split) w = J.W2[(int64_t)(n - J.n_split) * J.ldw + k];
     else w = J.W[(int64_t)n * J.ldw + k];
   }
@@ -1082,7 +1091,6 @@ static int tc_rows_chain_legacy_supported(const DnRowsSrc& src, const DnLayer* l
     const DnLayer& L = layers[l];
     if (L.K % 16 || L.K < 16 || L.N % 16 || L.N < 16 || L.N > 256) return DN_ERR_UNSUPPORTED;
     if (L.emul || L.relu_mask_src) return DN_ERR_UNSUPPORTED;
-    if (L.W2 && L.w_trans) return DN_ERR_UNSUPPORTED;
     if (L.bias && (reinterpret_cast<uintptr_t>(L.bias) & 15)) return DN_ERR_UNSUPPORTED;
     if (L.residual && (L.res_scale != 1.f || L.ld_res % 4 || (reinterpret_cast<uintptr_t>(L.residual) & 15)))
       return DN_ERR_UNSUPPORTED;
@@ -1129,7 +1137,7 @@ int tc_pack_layers_spectral(DnLayer* layers, int n_layers, void* ws, int64_t ws_
     J.W = L.W; J.W2 = L.W2; J.n_split = L.n_split; J.ldw = L.ldw; J.w_trans = L.w_trans; J.K = L.K; J.N = L.N;
     J.dst = reinterpret_cast<float*>(wp);
     J.blk0 = blocks;
-    blocks += (L.K * L.N + 255) / 256;
+    blocks += (l == 0 && partial) ? (L.K * L.N + 31) / 32 : (L.K * L.N + 255) / 256;
     L.prepacked = J.dst;
     wp += ((int64_t)L.K * L.N * 2 * 4 + 255) / 256 * 256;
   }

@@ -192,6 +192,42 @@ def test_block_backward_golden(dn, engine, name, kw):
         assert O.rel_err(prm.grad.cpu().numpy(), fx["g:" + n]) < 5e-5, n
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+def test_block_backward_config2_shape_vs_oracle_autograd(dn, engine):
+    """BASELINE config 2 shape (human-seg class: V ~ 7k, K = 128, C = 128): forward + backward of one block against
+    fp64 autograd through the torch restatement of the reference block (oracle/dn_oracle_torch.py, itself pinned to
+    the live reference by tests/test_oracle.py).  This is the shape the tensor-core backward (rows_chain3 dX layers,
+    split-V tcgen05 weight gradients) is built for.  Tolerances as in the golden backward test."""
+    import dn_oracle_torch as T
+    dn.set_engine(engine)
+    n, m, K, C = 84, 84, 128, 128
+    mass, L, evals, evecs, gX, gY = dn.synthetic.structural_operators(n, m, K, seed=3, device="cuda")
+    V = n * m
+    params = dn.synthetic.block_weights(C, seed=3)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(V, C, generator=g)
+    R = torch.randn(V, C, generator=g)
+    blk = dn.DiffusionNetBlock(C_width=C, mlp_hidden_dims=[C, C], dropout=False)
+    blk.load_state_dict(params, strict=True)
+    blk = blk.cuda().train()
+    xg = x.cuda().unsqueeze(0).requires_grad_(True)
+    out = blk(xg, mass.unsqueeze(0), None, evals.unsqueeze(0), evecs.unsqueeze(0), [gX], [gY])
+    (out[0] * R.cuda()).sum().backward()
+    # gold: fp64 on the CPU
+    d = torch.float64
+    prm = {k: v.to(d).requires_grad_(True) for k, v in params.items()}
+    x64 = x.to(d).unsqueeze(0).requires_grad_(True)
+    gxc, gyc = gX.cpu().to(d), gY.cpu().to(d)
+    gold = T.block_forward(x64, mass.cpu().to(d).unsqueeze(0), evals.cpu().to(d).unsqueeze(0),
+                           evecs.cpu().to(d).unsqueeze(0), [gxc], [gyc], prm)
+    (gold[0] * R.to(d)).sum().backward()
+    assert O.rel_err(out[0].detach().cpu().numpy(), gold[0].detach().numpy()) < TOL[engine]
+    assert O.rel_err(xg.grad[0].cpu().numpy(), x64.grad[0].numpy()) < 2e-5
+    for name, p_ in blk.named_parameters():
+        assert p_.grad is not None, name
+        assert O.rel_err(p_.grad.cpu().numpy(), prm[name].grad.numpy()) < 5e-5, name
+
+
 def test_errors_and_no_cpu_fallback(dn):
     blk = dn.DiffusionNetBlock(C_width=32, mlp_hidden_dims=[32, 32], dropout=False)
     x = torch.zeros(1, 10, 32)
