@@ -578,7 +578,6 @@ def main():
     roof, stages, kernels = None, None, None
     if rank == 0:
         pk = peaks()
-        tf32 = measure_tf32_peak(dev)
         gops = dn.prepare_operators(gradX, gradY)
         A_re, A_im = blk.gradient_features.weights()
         lins = blk.mlp.linears()
@@ -592,54 +591,6 @@ def main():
                 if it >= 2:
                     acc = [a + b for a, b in zip(acc, prof)]
         stages = {n + "_ms": a / nprof for n, a in zip(dn.ops.PROFILE_STAGES, acc)}
-        C, K = C_WIDTH, K_EIG
-        nnz = NNZ_ROW * V
-        passes = 3 if args.engine == "tc3x" else 1
-        # algorithmic (minimum) HBM bytes and useful fp32 flops per launch of each kernel (DESIGN.md section 4)
-        work = {
-            "to_basis": (4 * V * (K + C) + 4 * V, 2 * K * C * V, "to_basis_kernel (split-V tcgen05)"),
-            "spectral_scale": (4 * 148 * K * C, 0, "spectral_scale_kernel"),
-            "pack_weights": (3 * 4 * (K * C + 2 * C * C + 5 * C * C), 0, "pack_weights_kernel"),
-            "from_basis_pq": (4 * V * (K + C + 2 * C), (2 * K * C + 4 * C * C) * V,
-                              "rows_chain3_kernel (from_basis -> [P|Q], 2 fused layers)"),
-            "grad_features_gather": (4 * V * (3 * C + C) + 12 * nnz + 4 * V, 12 * NNZ_ROW * C * V,
-                                     "spmm_features_kernel (CSR gather + inner product + tanh)"),
-            "mlp": (4 * V * (3 * C + C), 10 * C * C * V, "rows_chain3_kernel (MiniMLP + skip, 3 fused layers)"),
-        }
-        try:   # per-launch DRAM traffic of each kernel from the committed ncu --set full capture of this command
-            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
-                traffic = json.load(fh)
-        except Exception:
-            traffic = {}
-        kernels = []
-        for name in dn.ops.PROFILE_STAGES:
-            ms = stages[name + "_ms"]
-            by, fl, kname = work[name]
-            gbs = by / (ms * 1e-3) / 1e9
-            tfl = fl / (ms * 1e-3) / 1e12
-            t_hbm = by / (pk["hbm_gbs"] * 1e9)
-            t_tc = passes * fl / (tf32["tf32_tflops"] * 1e12)
-            ent = {"stage": name, "kernel": kname, "ms": ms, "algorithmic_bytes": by, "useful_flops": fl,
-                   "achieved_gbs": gbs, "hbm_frac": gbs / pk["hbm_gbs"],
-                   "issued_tf32_tflops": passes * tfl, "tf32_frac": passes * tfl / tf32["tf32_tflops"],
-                   "bound": "tensor" if t_tc > t_hbm else "hbm", "floor_ms": max(t_tc, t_hbm) * 1e3,
-                   "traffic": traffic.get(name)}
-            kernels.append(ent)
-        dom = max(kernels, key=lambda e: e["ms"])
-        if dom["bound"] == "tensor":
-            roof = {"bound": "tensor", "achieved": dom["issued_tf32_tflops"], "peak": tf32["tf32_tflops"],
-                    "unit": "TFLOP/s", "frac": dom["tf32_frac"],
-                    "note": "kind::tf32 MMAs issued (3 per fp32 product in 3xTF32 mode) over the cuBLAS TF32 GEMM rate "
-                            "measured in this run (burst); useful fp32 flops are a third of `achieved`"}
-        else:
-            roof = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": dom["hbm_frac"],
-                    "note": "algorithmic bytes per launch / CUDA-event time over the measured copy bandwidth"}
-        roof.update({"kernel": dom["kernel"], "ms": dom["ms"], "traffic": dom["traffic"],
-                     "traffic_source": "profiles/r02_traffic.json (one ncu --set full launch of this command)",
-                     "peak_source": pk["source"], "tf32_peak": tf32, "bf16_peak_tflops": pk["bf16_tflops"],
-                     "block_hbm_frac": bytes_per_vertex(K_EIG, C) * V / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"],
-                     "block_tf32_frac": passes * (4 * K * C + 14 * C * C) * V / (ms_step * 1e-3) / 1e12 / tf32["tf32_tflops"]})
 
     # ---- the reference beside it (rank 0, N=1 only; bounded samples) ----
     cpu, gpu_base = None, None
@@ -675,6 +626,61 @@ def main():
         cpu = {"value": V / sec / 1e6, "unit": "Mverts/s", "cores": cores, "kind": kind,
                "sample": "same workload (1 mesh V=200000), 3 steps median, 1 warm-up; threads picked by a 1-step "
                          "sweep (seconds per step): {}".format(sweep)}
+
+    if rank == 0:
+        # the cuBLAS TF32 peak is measured LAST: a second of back-to-back GEMMs leaves the GPU power-capped for a while
+        # (it inflated the stage times by 1.5x when it ran before them)
+        tf32 = measure_tf32_peak(dev)
+        C, K = C_WIDTH, K_EIG
+        nnz = NNZ_ROW * V
+        passes = 3 if args.engine == "tc3x" else 1
+        # algorithmic (minimum) HBM bytes and useful fp32 flops per launch of each kernel (DESIGN.md section 4)
+        work = {
+            "to_basis": (4 * V * (K + C) + 4 * V, 2 * K * C * V, "to_basis_kernel (split-V tcgen05)"),
+            "spectral_scale": (0, 0, "(separate launch only on the SIMT engine; part of pack_weights_kernel here)"),
+            "pack_weights": (4 * 148 * K * C + 3 * 4 * (K * C + 2 * C * C + 5 * C * C), 0,
+                             "pack_weights_kernel (split-V partial reduction + exp(-lambda t) scale + hi/lo weight pack)"),
+            "from_basis_pq": (4 * V * (K + C + 2 * C), (2 * K * C + 4 * C * C) * V,
+                              "rows_chain3_kernel (from_basis -> [P|Q], 2 fused layers)"),
+            "grad_features_gather": (4 * V * (3 * C + C) + 12 * nnz + 4 * V, 12 * NNZ_ROW * C * V,
+                                     "spmm_features_kernel (CSR gather + inner product + tanh)"),
+            "mlp": (4 * V * (3 * C + C), 10 * C * C * V, "rows_chain3_kernel (MiniMLP + skip, 3 fused layers)"),
+        }
+        try:   # per-launch DRAM traffic of each kernel from the committed ncu --set full capture of this command
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
+                traffic = json.load(fh)
+        except Exception:
+            traffic = {}
+        kernels = []
+        for name in dn.ops.PROFILE_STAGES:
+            ms = stages[name + "_ms"]
+            by, fl, kname = work[name]
+            ms = max(ms, 1e-6)
+            gbs = by / (ms * 1e-3) / 1e9
+            tfl = fl / (ms * 1e-3) / 1e12
+            t_hbm = by / (pk["hbm_gbs"] * 1e9)
+            t_tc = passes * fl / (tf32["tf32_tflops"] * 1e12)
+            ent = {"stage": name, "kernel": kname, "ms": ms, "algorithmic_bytes": by, "useful_flops": fl,
+                   "achieved_gbs": gbs, "hbm_frac": gbs / pk["hbm_gbs"],
+                   "issued_tf32_tflops": passes * tfl, "tf32_frac": passes * tfl / tf32["tf32_tflops"],
+                   "bound": "tensor" if t_tc > t_hbm else "hbm", "floor_ms": max(t_tc, t_hbm) * 1e3,
+                   "traffic": traffic.get(name)}
+            kernels.append(ent)
+        dom = max(kernels, key=lambda e: e["ms"])
+        if dom["bound"] == "tensor":
+            roof = {"bound": "tensor", "achieved": dom["issued_tf32_tflops"], "peak": tf32["tf32_tflops"],
+                    "unit": "TFLOP/s", "frac": dom["tf32_frac"],
+                    "note": "kind::tf32 MMAs issued (3 per fp32 product in 3xTF32 mode) over the cuBLAS TF32 GEMM rate "
+                            "measured in this run (burst); useful fp32 flops are a third of `achieved`"}
+        else:
+            roof = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": dom["hbm_frac"],
+                    "note": "algorithmic bytes per launch / CUDA-event time over the measured copy bandwidth"}
+        roof.update({"kernel": dom["kernel"], "ms": dom["ms"], "traffic": dom["traffic"],
+                     "traffic_source": "profiles/r02_traffic.json (one ncu --set full launch of this command)",
+                     "peak_source": pk["source"], "tf32_peak": tf32, "bf16_peak_tflops": pk["bf16_tflops"],
+                     "block_hbm_frac": bytes_per_vertex(K_EIG, C) * V / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+                     "block_tf32_frac": passes * (4 * K * C + 14 * C * C) * V / (ms_step * 1e-3) / 1e12 / tf32["tf32_tflops"]})
 
     if rank == 0:
         print(json.dumps({

@@ -65,7 +65,9 @@ struct C3Layer {
 
 struct C3Params {
   C3Layer layer[DN_MAX_LAYERS];
-  int n_layers, passes, nsrc;
+  int n_layers, nsrc;
+  int passes;      // 1: one TF32 MMA per product | 3: 3xTF32 (lo*hi + hi*lo + hi*hi) | 2: TF32 hi*hi + bf16 corrections
+  int fmt;         // packed-weight layout (DnLayer::pack_fmt): passes 3 needs 0, passes 2 needs 1, passes 1 takes either
   int src_width[DN_MAX_SRC];
   int nbuf;        // accumulator buffers (2: ping-pong, column 128 * (g & 1); 1: column 0)
   int ring_col;    // first TMEM column of the operand ring
@@ -242,7 +244,7 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
       for (int l = 0; l < L; ++l, ++g) {
         const int N = p.layer[l].N, nst = p.layer[l].K / C3_KS;
-        const uint32_t idesc = make_idesc_tf32(C3_TILE, N);
+        const uint32_t idesc = make_idesc_tf32(C3_TILE, N), idesc16 = make_idesc_bf16(C3_TILE, N);
         const uint32_t buf = two ? (g & 1u) : 0u;
         const uint32_t d_tmem = tmem_base + buf * 128u;
         const uint32_t b_lbo = (uint32_t)N * 16u;
@@ -269,17 +271,32 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
           if (elect_one()) {
             const uint32_t a0 = tmem_base + (uint32_t)p.ring_col + s * 64u;
             const uint64_t dbs = tmplB + (w_u4 + s * (w_slot >> 4));
+            if (p.passes == 2) {
+              // stage = [tf32 hi image | bf16 (hi ; lo) image], k-group stride N * 16 B in both.  Four TF32 MMAs (K = 8)
+              // form hi*hi; four bf16 MMAs (K = 16) add the corrections [x_lo | x_hi] . [W_hi ; W_lo] -- 8 instructions and
+              // 32 KiB of shared-memory operand reads per stage where 3xTF32 needs 12 and 48 KiB, same fp32-grade result
+              const uint32_t kg2 = (2u * b_lbo) >> 4;
 #pragma unroll
-            for (int ks = 0; ks < C3_KS / 8; ++ks) {
-              const uint32_t a_hi = a0 + ks * 8, a_lo = a_hi + 32;
-              const uint64_t b_h = dbs + (uint32_t)(ks >> 1) * b_chunk_u + (uint32_t)(ks & 1) * b_ks_u;
-              const uint32_t acc = (c | ks) ? 1u : 0u;
-              if (p.passes == 3) {
-                mma_tf32_ts(d_tmem, a_lo, b_h, idesc, acc);
-                mma_tf32_ts(d_tmem, a_hi, b_h + b_img_u, idesc, 1u);
-                mma_tf32_ts(d_tmem, a_hi, b_h, idesc, 1u);
-              } else {
-                mma_tf32_ts(d_tmem, a_hi, b_h, idesc, acc);
+              for (int ks = 0; ks < 4; ++ks)
+                mma_tf32_ts(d_tmem, a0 + ks * 8, dbs + (uint32_t)ks * kg2, idesc, (c | ks) ? 1u : 0u);
+              const uint64_t db16 = dbs + (((uint32_t)N * 128u) >> 4);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                mma_f16_ts(d_tmem, a0 + 32 + j * 8, db16 + (uint32_t)j * kg2, idesc16, 1u);
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < C3_KS / 8; ++ks) {
+                const uint32_t a_hi = a0 + ks * 8, a_lo = a_hi + 32;
+                const uint64_t b_h = p.fmt ? dbs + (uint32_t)ks * b_ks_u
+                                           : dbs + (uint32_t)(ks >> 1) * b_chunk_u + (uint32_t)(ks & 1) * b_ks_u;
+                const uint32_t acc = (c | ks) ? 1u : 0u;
+                if (p.passes == 3) {
+                  mma_tf32_ts(d_tmem, a_lo, b_h, idesc, acc);
+                  mma_tf32_ts(d_tmem, a_hi, b_h + b_img_u, idesc, 1u);
+                  mma_tf32_ts(d_tmem, a_hi, b_h, idesc, 1u);
+                } else {
+                  mma_tf32_ts(d_tmem, a_hi, b_h, idesc, acc);
+                }
               }
             }
             mma_commit(ab_empty + 8 * s);             // frees TMEM operand stage s and weight stage s
@@ -314,13 +331,32 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
       C3_TRACE(4);
       tc_fence_after();
       const uint32_t ta = lane_base + (uint32_t)p.ring_col + s * 64u;
+      if (p.passes == 2) {
+        // columns [0,32): tf32 hi | [32,48): bf16x2 pairs of lo = x - hi | [48,64): bf16x2 pairs of hi
+        float plo[16], phi[16];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float hi[16], lo[16];
+        for (int h = 0; h < 2; ++h) {
+          float hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) split_tf32_fast(x[16 * h + j], hi[j], lo[j]);
-        tmem_st16(ta + 16 * h, hi);
-        if (p.passes == 3) tmem_st16(ta + 32 + 16 * h, lo);
+          for (int j = 0; j < 16; ++j) split_tf32_fast(x[16 * h + j], hi[j], lo[j]);
+          tmem_st16(ta + 16 * h, hi);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            plo[8 * h + j] = __uint_as_float(pack_bf16x2(lo[2 * j], lo[2 * j + 1]));
+            phi[8 * h + j] = __uint_as_float(pack_bf16x2(hi[2 * j], hi[2 * j + 1]));
+          }
+        }
+        tmem_st16(ta + 32, plo);
+        tmem_st16(ta + 48, phi);
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) split_tf32_fast(x[16 * h + j], hi[j], lo[j]);
+          tmem_st16(ta + 16 * h, hi);
+          if (p.passes == 3) tmem_st16(ta + 32 + 16 * h, lo);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -641,6 +677,11 @@ int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, in
   memset(&maps, 0, sizeof(maps));
   p.n_layers = n_layers;
   p.passes = passes;
+  for (int l = 0; l < n_layers; ++l)
+    if (layers[l].pack_fmt != layers[0].pack_fmt) return DN_ERR_INVALID_ARGUMENT;
+  p.fmt = layers[0].pack_fmt;
+  if (p.fmt == 1) p.passes = (passes == 3) ? 2 : 1;                 // stage layout [tf32 hi | bf16 (hi ; lo)]
+
   p.V = V;
   p.trace = trace;
   p.nsrc = src.nsrc;

@@ -33,6 +33,8 @@ struct DnLayer {
   const float* W2;       // optional second block: !w_trans: output rows n >= n_split come from W2[n - n_split]
   int n_split;           //   (stacks [A_re; A_im] without a copy);  w_trans: input rows k >= n_split come from W2[k - n_split]
   const float* prepacked;  // optional: weights already in the tensor-core layout (tc_pack_layers)
+  int pack_fmt;            // layout of `prepacked`: 0 = 16-wide chunks of [tf32 hi | tf32 lo] (round-1 kernels, 3xTF32);
+                           //   1 = 32-wide stages of [tf32 hi | bf16 (hi ; lo)] (rows_chain3_kernel, TF32 + bf16 corrections)
   const float* bias;     // [N] or null
   int relu;
   const float* emul;     // optional elementwise multiplier [V][N] applied after the activation
@@ -99,6 +101,8 @@ bool tc_supported_device();
 int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers, int n_layers, int64_t V, int passes /*3 or 1*/,
                   void* ws, int64_t ws_bytes, cudaStream_t st);
 int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers);
+// packed-weight layout the kernel that will run this chain expects (sets layers[i].pack_fmt; call before tc_pack_layers)
+void tc_choose_pack_fmt(const DnRowsSrc& src, DnLayer* layers, int n_layers);
 // partial[p][k][c] for p < *P_out
 int tc_to_basis_partial(const float* values, const float* basis, const float* massvec, int64_t V, int K, int C,
                         float* partial, int* P_out, int passes, cudaStream_t st);

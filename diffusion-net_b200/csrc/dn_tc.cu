@@ -17,6 +17,7 @@
 #include "dn_internal.h"
 #include "dn_tc_ptx.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -67,7 +68,7 @@ struct PackJob {
   const float* W2;
   float* dst;
   int64_t ldw;
-  int n_split, w_trans, K, N, blk0;
+  int n_split, w_trans, K, N, blk0, fmt;
 };
 struct PackJobs {
   PackJob j[DN_MAX_LAYERS];
@@ -120,6 +121,19 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackJobs jobs) {
   }
   float hi, lo;
   split_tf32(w, hi, lo);
+  if (J.fmt == 1) {
+    // 32-wide stage = [tf32 hi image: 8 k-groups of 4 | bf16 image: 4 k-groups of 8 of bf16(hi), then 4 of bf16(lo)],
+    // both K-major canonical (no swizzle): k-group stride N * 16 B, 8-row group stride 128 B, row stride 16 B
+    const int st = k >> 5, kk = k & 31;
+    char* base = reinterpret_cast<char*>(J.dst) + (int64_t)st * N * 256;
+    const int64_t rowoff = (int64_t)(n >> 3) * 128 + (n & 7) * 16;
+    *reinterpret_cast<float*>(base + (int64_t)(kk >> 2) * N * 16 + rowoff + (kk & 3) * 4) = hi;
+    char* b16 = base + (int64_t)N * 128;
+    *reinterpret_cast<__nv_bfloat16*>(b16 + (int64_t)(kk >> 3) * N * 16 + rowoff + (kk & 7) * 2) = __float2bfloat16_rn(hi);
+    *reinterpret_cast<__nv_bfloat16*>(b16 + (int64_t)(4 + (kk >> 3)) * N * 16 + rowoff + (kk & 7) * 2) =
+        __float2bfloat16_rn(w - hi);
+    return;
+  }
   const int chunk = k / kc, kk = k % kc;
   const int64_t img = (int64_t)N * kc;   // floats per image
   const int64_t off = (int64_t)chunk * 2 * img + (int64_t)(kk >> 2) * (N * 4) + (n >> 3) * 32 + (n & 7) * 4 + (kk & 3);
@@ -1110,6 +1124,20 @@ int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_l
   return tc_rows_chain_legacy_supported(src, layers, n_layers);
 }
 
+static bool hybrid_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DN_TC_HYBRID");
+    on = (!e || atoi(e) != 0) ? 1 : 0;
+  }
+  return on == 1;
+}
+
+void tc_choose_pack_fmt(const DnRowsSrc& src, DnLayer* layers, int n_layers) {
+  const int fmt = (hybrid_enabled() && tc_chain3_supported(src, layers, n_layers) == DN_OK) ? 1 : 0;
+  for (int l = 0; l < n_layers; ++l) layers[l].pack_fmt = fmt;
+}
+
 int64_t tc_chain_ws_bytes(const DnLayer* layers, int n_layers) {
   int64_t b = 0;
   for (int l = 0; l < n_layers; ++l) b += ((int64_t)layers[l].K * layers[l].N * 2 * 4 + 255) / 256 * 256;
@@ -1135,6 +1163,7 @@ int tc_pack_layers_spectral(DnLayer* layers, int n_layers, void* ws, int64_t ws_
     DnLayer& L = layers[l];
     PackJob& J = jobs.j[l];
     J.W = L.W; J.W2 = L.W2; J.n_split = L.n_split; J.ldw = L.ldw; J.w_trans = L.w_trans; J.K = L.K; J.N = L.N;
+    J.fmt = L.pack_fmt;
     J.dst = reinterpret_cast<float*>(wp);
     J.blk0 = blocks;
     blocks += (l == 0 && partial) ? (L.K * L.N + 31) / 32 : (L.K * L.N + 255) / 256;
@@ -1158,6 +1187,7 @@ int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers_in, int n_layers, 
     packed = packed && layers[l].prepacked != nullptr;
   }
   if (!packed) {
+    tc_choose_pack_fmt(src, layers, n_layers);
     int rc = tc_pack_layers(layers, n_layers, ws, ws_bytes, st);
     if (rc) return rc;
   }
@@ -1166,6 +1196,8 @@ int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers_in, int n_layers, 
     const int rc = tc_rows_chain3(src, layers, n_layers, V, passes, dv->sms, take_trace_ptr(), st);
     if (rc != DN_ERR_UNSUPPORTED) return rc;
   }
+  for (int l = 0; l < n_layers; ++l)
+    if (layers[l].pack_fmt != 0) return DN_ERR_INVALID_ARGUMENT;     // the round-1 kernels read the 16-wide chunk layout
   if (tc_rows_chain_legacy_supported(src, layers, n_layers) != DN_OK) return DN_ERR_UNSUPPORTED;
   TcChainParams p;
   memset(&p, 0, sizeof(p));

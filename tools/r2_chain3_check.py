@@ -106,8 +106,23 @@ def check_block(V_n, V_m, reps=3, timing=False):
     return res
 
 
+def check_shapes(V=5000):
+    """Envelope sweep: chains of Linear(+ReLU) with random weights, tc3x vs the exact SIMT engine."""
+    g = torch.Generator().manual_seed(11)
+    for dims in ([128, 256], [128, 128], [128, 64], [128, 32], [64, 128], [256, 128], [256, 256], [192, 96],
+                 [128, 128, 256], [128, 64, 128], [384, 128, 128, 128], [64, 64, 64, 64, 64], [128, 128, 128, 128, 128, 128, 128]):
+        x = torch.randn(V, dims[0], generator=g).cuda()
+        ws = [((torch.rand(dims[i + 1], dims[i], generator=g) * 2 - 1) / dims[i] ** 0.5).cuda() for i in range(len(dims) - 1)]
+        bs = [((torch.rand(dims[i + 1], generator=g) * 2 - 1) / dims[i] ** 0.5).cuda() for i in range(len(dims) - 1)]
+        with torch.no_grad():
+            dn.set_engine("simt"); y0 = dn.ops.mlp_apply([x], ws, bs)
+            dn.set_engine("tc3x"); y1 = dn.ops.mlp_apply([x], ws, bs)
+        print("   dims {}: rel err {:.2e}".format(dims, rel(y1, y0)), flush=True)
+
+
 if __name__ == "__main__":
     print("DN_TC_CHAIN3 =", os.environ.get("DN_TC_CHAIN3", "1 (default)"), flush=True)
+    check_shapes()
     for V in (100, 128, 129, 1000, 18944, 18945, 40000):
         print("V={:6d}: {}".format(V, check(V)), flush=True)
     print("V=200000:", check(200000, reps=6, timing=True), flush=True)
