@@ -421,20 +421,6 @@ __global__ void __launch_bounds__(256) spmm_features_kernel(const int32_t* __res
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Default gather at C = 128: persistent warps, 16 consecutive rows per warp visit, software-pipelined metadata,
-// packed fp32x2 FMAs.
-//   * the round-1 kernel (one short-lived warp per row) issued ~530 warp instructions per row and spent 53 % of its
-//     cycles issuing: here the 24 FFMA per (neighbour, float4) become 12 FFMA2 (fma.rn.f32x2 -- two IEEE fp32 FMAs per
-//     instruction, bit-identical results), tanhf becomes feat_tanh, and P, Q share one address computation;
-//   * a row's (col, gx, gy) triples are fetched by the lanes in ONE coalesced load each, one row ahead of use, and
-//     broadcast with shuffles: the neighbour-row gathers never wait on a dependent index load;
-//   * a warp walks 16 consecutive rows, so a row re-reads most of its predecessor's neighbour rows out of L1.
-// Entry order = CSR order and the arithmetic per element is the same fmaf sequence as gather_row.
-// ---------------------------------------------------------------------------------------------
-constexpr int GP_ROWS = 16;     // consecutive rows per warp visit
-
-
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
   unsigned long long r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -448,97 +434,95 @@ __device__ __forceinline__ void fma2(unsigned long long& d, unsigned long long a
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }
 
-// GP_NB: neighbour rows gathered per batch (3 * GP_NB independent 16-byte loads per lane); MINB: CTAs per SM the
-// register budget is sized for
-template <bool ROT, int GP_NB, int MINB>
+// ---------------------------------------------------------------------------------------------
+// Block gather (C = 128): one CTA per 64 consecutive rows.
+//   * the block's CSR metadata (rowptr slice, every (col, gx, gy) triple) is staged in shared memory by ONE coalesced
+//     pass: the per-row dependent chain rowptr -> colidx -> neighbour rows (three DRAM/L2 latencies in the warp-per-row
+//     kernel) becomes one latency per 64 rows plus the gathers themselves;
+//   * a warp issues every neighbour-row load of a batch of NB entries (3 x NB independent 16-byte loads per lane)
+//     before the first FMA; 8 warps walk 8 consecutive rows at a time, so the band structure of a locally ordered
+//     mesh hits L1;
+//   * packed fp32x2 FMAs (fma.rn.f32x2: two IEEE fp32 FMAs per instruction, bit-identical to fmaf).
+// Entry order = CSR order and the arithmetic per element is the same fmaf sequence as gather_row: bit-identical output.
+// ---------------------------------------------------------------------------------------------
+constexpr int GB_ROWS = 64;      // rows per CTA
+constexpr int GB_NNZ = 1024;     // staged entries per CTA (entries past it are read from global memory)
+
+template <bool ROT, int NB, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-spmm_features_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                          const float2* __restrict__ vals, const float* __restrict__ xd,
-                          const float* __restrict__ pq, int ld_pq, int64_t V, float* __restrict__ feat) {
+spmm_features_blk_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                         const float2* __restrict__ vals, const float* __restrict__ xd,
+                         const float* __restrict__ pq, int ld_pq, int64_t V, float* __restrict__ feat) {
   constexpr int C = 128;
-  const int lane = threadIdx.x & 31;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int64_t nblk = (V + GP_ROWS - 1) / GP_ROWS;
+  __shared__ int s_rp[GB_ROWS + 1];
+  __shared__ int s_col[GB_NNZ];
+  __shared__ float2 s_g[GB_NNZ];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = (int64_t)blockIdx.x * GB_ROWS;
+  const int nrows = (int)((V - base) < GB_ROWS ? (V - base) : GB_ROWS);
+  if ((int)threadIdx.x <= nrows) s_rp[threadIdx.x] = __ldg(rowptr + base + threadIdx.x);
+  __syncthreads();
+  const int e0 = s_rp[0];
+  {
+    const int tot = s_rp[nrows] - e0;
+    const int cnt = tot < GB_NNZ ? tot : GB_NNZ;
+    for (int i = threadIdx.x; i < cnt; i += 256) {
+      s_col[i] = __ldg(colidx + e0 + i);
+      s_g[i] = __ldg(vals + e0 + i);
+    }
+  }
+  __syncthreads();
   const char* xb = reinterpret_cast<const char*>(xd) + lane * 16;
   const char* pb = reinterpret_cast<const char*>(pq) + lane * 16;
   const int64_t pq_row_bytes = (int64_t)ld_pq * 4;
-  for (int64_t blk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < nblk; blk += nwarps) {
-    const int64_t base = blk * GP_ROWS;
-    const int nrows = (int)((V - base) < GP_ROWS ? (V - base) : GP_ROWS);
-    // rowptr[base .. base+16] held by lanes 0..16
-    const int rp = (lane <= nrows) ? __ldg(rowptr + base + lane) : 0;
-    int s = __shfl_sync(0xffffffffu, rp, 0), e = __shfl_sync(0xffffffffu, rp, 1);
-    int mycol = 0;
-    float2 myg = make_float2(0.f, 0.f);
-    if (lane < e - s) { mycol = __ldg(colidx + s + lane); myg = __ldg(vals + s + lane); }
-    for (int r = 0; r < nrows; ++r) {
-      const int n = e - s;
-      // next row's triples: in flight while this row is gathered
-      int s2 = 0, e2 = 0, col2 = 0;
-      float2 g2 = make_float2(0.f, 0.f);
-      if (r + 1 < nrows) {
-        s2 = __shfl_sync(0xffffffffu, rp, r + 1);
-        e2 = __shfl_sync(0xffffffffu, rp, r + 2);
-        if (lane < e2 - s2) { col2 = __ldg(colidx + s2 + lane); g2 = __ldg(vals + s2 + lane); }
-      }
-      unsigned long long gX0 = 0ull, gX1 = 0ull, gY0 = 0ull, gY1 = 0ull, re0 = 0ull, re1 = 0ull, im0 = 0ull, im1 = 0ull;
-      for (int b0 = 0; b0 < n; b0 += 32) {                       // rows longer than a warp: 32 entries at a time
-        int col_l = mycol;
-        float2 g_l = myg;
-        if (b0 > 0) {
-          col_l = 0; g_l = make_float2(0.f, 0.f);
-          if (b0 + lane < n) { col_l = __ldg(colidx + s + b0 + lane); g_l = __ldg(vals + s + b0 + lane); }
+  for (int r = warp; r < nrows; r += 8) {
+    const int s = s_rp[r] - e0, e = s_rp[r + 1] - e0;
+    unsigned long long gX0 = 0ull, gX1 = 0ull, gY0 = 0ull, gY1 = 0ull, re0 = 0ull, re1 = 0ull, im0 = 0ull, im1 = 0ull;
+    for (int p0 = s; p0 < e; p0 += NB) {
+      ulonglong2 x[NB], P[NB], Q[NB];
+      float wx[NB], wy[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int p = p0 + j;
+        if (p < e) {                                             // (warp-uniform)
+          int col;
+          float2 g;
+          if (p < GB_NNZ) { col = s_col[p]; g = s_g[p]; }
+          else { col = __ldg(colidx + e0 + p); g = __ldg(vals + e0 + p); }
+          wx[j] = g.x; wy[j] = g.y;
+          x[j] = __ldg(reinterpret_cast<const ulonglong2*>(xb + (int64_t)col * (C * 4)));
+          const char* pr = pb + (int64_t)col * pq_row_bytes;
+          P[j] = __ldg(reinterpret_cast<const ulonglong2*>(pr));
+          if (ROT) Q[j] = __ldg(reinterpret_cast<const ulonglong2*>(pr + C * 4));
         }
-        const int cnt = (n - b0) < 32 ? (n - b0) : 32;
-        for (int p0 = 0; p0 < cnt; p0 += GP_NB) {
-          ulonglong2 x[GP_NB], P[GP_NB], Q[GP_NB];
-          float wx[GP_NB], wy[GP_NB];
+      }
 #pragma unroll
-          for (int j = 0; j < GP_NB; ++j) {
-            const int pj = (p0 + j < cnt) ? p0 + j : p0;
-            const int64_t col = __shfl_sync(0xffffffffu, col_l, pj);
-            wx[j] = __shfl_sync(0xffffffffu, g_l.x, pj);
-            wy[j] = __shfl_sync(0xffffffffu, g_l.y, pj);
-            if (p0 + j < cnt) {
-              x[j] = __ldg(reinterpret_cast<const ulonglong2*>(xb + col * (C * 4)));
-              const char* pr = pb + col * pq_row_bytes;
-              P[j] = __ldg(reinterpret_cast<const ulonglong2*>(pr));
-              if (ROT) Q[j] = __ldg(reinterpret_cast<const ulonglong2*>(pr + C * 4));
-            } else {
-              x[j] = make_ulonglong2(0ull, 0ull); P[j] = x[j]; Q[j] = x[j];
-              wx[j] = 0.f; wy[j] = 0.f;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < GP_NB; ++j) {
-            if (p0 + j < cnt) {                                    // (warp-uniform)
-              const unsigned long long gx2 = pack2(wx[j], wx[j]), gy2 = pack2(wy[j], wy[j]);
-              fma2(gX0, gx2, x[j].x); fma2(gX1, gx2, x[j].y);
-              fma2(gY0, gy2, x[j].x); fma2(gY1, gy2, x[j].y);
-              fma2(re0, gx2, P[j].x); fma2(re1, gx2, P[j].y);
-              fma2(im0, gy2, P[j].x); fma2(im1, gy2, P[j].y);
-              if (ROT) {
-                const unsigned long long ngy2 = pack2(-wy[j], -wy[j]);
-                fma2(re0, ngy2, Q[j].x); fma2(re1, ngy2, Q[j].y);
-                fma2(im0, gx2, Q[j].x); fma2(im1, gx2, Q[j].y);
-              }
-            }
+      for (int j = 0; j < NB; ++j) {
+        if (p0 + j < e) {
+          const unsigned long long gx2 = pack2(wx[j], wx[j]), gy2 = pack2(wy[j], wy[j]);
+          fma2(gX0, gx2, x[j].x); fma2(gX1, gx2, x[j].y);
+          fma2(gY0, gy2, x[j].x); fma2(gY1, gy2, x[j].y);
+          fma2(re0, gx2, P[j].x); fma2(re1, gx2, P[j].y);
+          fma2(im0, gy2, P[j].x); fma2(im1, gy2, P[j].y);
+          if (ROT) {
+            const unsigned long long ngy2 = pack2(-wy[j], -wy[j]);
+            fma2(re0, ngy2, Q[j].x); fma2(re1, ngy2, Q[j].y);
+            fma2(im0, gx2, Q[j].x); fma2(im1, gx2, Q[j].y);
           }
         }
       }
-      float gXv[4], gYv[4], rev[4], imv[4];
-      unpack2(gX0, gXv[0], gXv[1]); unpack2(gX1, gXv[2], gXv[3]);
-      unpack2(gY0, gYv[0], gYv[1]); unpack2(gY1, gYv[2], gYv[3]);
-      unpack2(re0, rev[0], rev[1]); unpack2(re1, rev[2], rev[3]);
-      unpack2(im0, imv[0], imv[1]); unpack2(im1, imv[2], imv[3]);
-      float4 o;
-      o.x = feat_tanh(fmaf(gXv[0], rev[0], gYv[0] * imv[0]));
-      o.y = feat_tanh(fmaf(gXv[1], rev[1], gYv[1] * imv[1]));
-      o.z = feat_tanh(fmaf(gXv[2], rev[2], gYv[2] * imv[2]));
-      o.w = feat_tanh(fmaf(gXv[3], rev[3], gYv[3] * imv[3]));
-      *reinterpret_cast<float4*>(feat + (base + r) * C + lane * 4) = o;
-      s = s2; e = e2; mycol = col2; myg = g2;
     }
+    float gXv[4], gYv[4], rev[4], imv[4];
+    unpack2(gX0, gXv[0], gXv[1]); unpack2(gX1, gXv[2], gXv[3]);
+    unpack2(gY0, gYv[0], gYv[1]); unpack2(gY1, gYv[2], gYv[3]);
+    unpack2(re0, rev[0], rev[1]); unpack2(re1, rev[2], rev[3]);
+    unpack2(im0, imv[0], imv[1]); unpack2(im1, imv[2], imv[3]);
+    float4 o;
+    o.x = feat_tanh(fmaf(gXv[0], rev[0], gYv[0] * imv[0]));
+    o.y = feat_tanh(fmaf(gXv[1], rev[1], gYv[1] * imv[1]));
+    o.z = feat_tanh(fmaf(gXv[2], rev[2], gYv[2] * imv[2]));
+    o.w = feat_tanh(fmaf(gXv[3], rev[3], gYv[3] * imv[3]));
+    *reinterpret_cast<float4*>(feat + (base + r) * C + lane * 4) = o;
   }
 }
 
@@ -654,190 +638,7 @@ __global__ void __launch_bounds__(512) spmm_features_patch_kernel(const dn_patch
   }
 }
 
-// Same patch gather with the copy and the gather overlapped: a persistent CTA (16 gather warps + 1 producer warp)
-// keeps TWO patches' rows in shared memory; the producer fetches them with bulk-async copies (cp.async.bulk, one per
-// row of x_diffuse and of [P|Q], mbarrier complete_tx), so no row passes through registers and the gather of patch k
-// runs while patch k+1 streams in.
-// STATUS: written at the end of round 1, compiled, NOT yet run on hardware -- opt-in only (DN_SPMM_PATCH_V=3);
-// the arithmetic and entry order are the validated kernel's.
-constexpr int PA_GATHER_WARPS = 16;
-constexpr int PA_THREADS = 32 * (PA_GATHER_WARPS + 1);
-
-template <bool ROT>
-__global__ void __launch_bounds__(PA_THREADS, 1)
-spmm_features_patch_async_kernel(const dn_patches P, const float* __restrict__ xd, const float* __restrict__ pq,
-                                 int ld_pq, int C, int buf_rows, float* __restrict__ feat) {
-  extern __shared__ __align__(128) uint8_t smraw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int xq = C >> 2, pqq = ld_pq >> 2, rowf4 = xq + pqq;
-  const uint32_t rowbytes = (uint32_t)rowf4 * 16u, bufbytes = (uint32_t)buf_rows * rowbytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + 2 * (size_t)bufbytes);
-  const uint32_t full = tc::smem_u32(bars), empty = tc::smem_u32(bars + 2);
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(full + 8 * i, 1); tc::mbar_init(empty + 8 * i, PA_GATHER_WARPS); }
-    tc::fence_barrier_init();
-  }
-  __syncthreads();
-  const float2* vals = reinterpret_cast<const float2*>(P.vals);
-  if (warp == PA_GATHER_WARPS) {
-    // ---- producer: rows of patch k -> buffer k & 1
-    uint32_t k = 0;
-    for (int p = blockIdx.x; p < P.n_patches; p += gridDim.x, ++k) {
-      const uint32_t b = k & 1, ph = (k >> 1) & 1;
-      const int s0 = __ldg(P.src_ptr + p), ns = __ldg(P.src_ptr + p + 1) - s0;
-      tc::mbar_wait(empty + 8 * b, ph ^ 1);
-      if (lane == 0) tc::mbar_arrive_expect_tx(full + 8 * b, (uint32_t)ns * rowbytes);
-      __syncwarp();
-      const uint32_t dst0 = tc::smem_u32(smraw) + b * bufbytes;
-      for (int r = lane; r < ns; r += 32) {
-        const int64_t row = __ldg(P.src_rows + s0 + r);
-        tc::tma_bulk_g2s(dst0 + (uint32_t)r * rowbytes, xd + row * C, (uint32_t)C * 4u, full + 8 * b);
-        tc::tma_bulk_g2s(dst0 + (uint32_t)r * rowbytes + (uint32_t)C * 4u, pq + row * ld_pq, (uint32_t)ld_pq * 4u,
-                         full + 8 * b);
-      }
-    }
-    return;
-  }
-  // ---- gather warps
-  struct Meta { int64_t row; int es, n; int lc; float2 g; };
-  uint32_t k = 0;
-  for (int p = blockIdx.x; p < P.n_patches; p += gridDim.x, ++k) {
-    const uint32_t b = k & 1, ph = (k >> 1) & 1;
-    const int t0 = __ldg(P.tgt_ptr + p), nt = __ldg(P.tgt_ptr + p + 1) - t0;
-    auto load_meta = [&](int i) {
-      Meta m;
-      m.row = 0; m.es = 0; m.n = 0; m.lc = 0; m.g = make_float2(0.f, 0.f);
-      if (i < nt) {
-        m.row = __ldg(P.tgt + t0 + i);
-        m.es = __ldg(P.ent_ptr + t0 + i);
-        m.n = __ldg(P.ent_ptr + t0 + i + 1) - m.es;
-        if (lane < m.n) { m.lc = __ldg(P.lcol + m.es + lane); m.g = __ldg(vals + m.es + lane); }
-      }
-      return m;
-    };
-    Meta cur = load_meta(warp);                                  // in flight while the rows land
-    tc::mbar_wait(full + 8 * b, ph);
-    const float4* sm4 = reinterpret_cast<const float4*>(smraw + (size_t)b * bufbytes);
-    for (int i = warp; i < nt; i += PA_GATHER_WARPS) {
-      const Meta nxt = load_meta(i + PA_GATHER_WARPS);
-      for (int c4 = lane; c4 < xq; c4 += 32) {                   // (C == 128: one iteration, every lane active)
-        Acc4 a;
-        a.gX = a.gY = a.bre = a.bim = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int base = 0; base < cur.n; base += 32) {
-          int lc_l = cur.lc;
-          float2 g_l = cur.g;
-          if (base > 0) {
-            lc_l = 0; g_l = make_float2(0.f, 0.f);
-            if (base + lane < cur.n) { lc_l = __ldg(P.lcol + cur.es + base + lane); g_l = __ldg(vals + cur.es + base + lane); }
-          }
-          const int cnt = (cur.n - base) < 32 ? (cur.n - base) : 32;
-          for (int e = 0; e < cnt; ++e) {
-            const int lc = __shfl_sync(0xffffffffu, lc_l, e);
-            float2 g;
-            g.x = __shfl_sync(0xffffffffu, g_l.x, e);
-            g.y = __shfl_sync(0xffffffffu, g_l.y, e);
-            const float4* src = sm4 + (size_t)lc * rowf4;
-            const float4 x = src[c4];
-            const float4 Pv = src[xq + c4];
-            a.gX.x = fmaf(g.x, x.x, a.gX.x); a.gX.y = fmaf(g.x, x.y, a.gX.y);
-            a.gX.z = fmaf(g.x, x.z, a.gX.z); a.gX.w = fmaf(g.x, x.w, a.gX.w);
-            a.gY.x = fmaf(g.y, x.x, a.gY.x); a.gY.y = fmaf(g.y, x.y, a.gY.y);
-            a.gY.z = fmaf(g.y, x.z, a.gY.z); a.gY.w = fmaf(g.y, x.w, a.gY.w);
-            a.bre.x = fmaf(g.x, Pv.x, a.bre.x); a.bre.y = fmaf(g.x, Pv.y, a.bre.y);
-            a.bre.z = fmaf(g.x, Pv.z, a.bre.z); a.bre.w = fmaf(g.x, Pv.w, a.bre.w);
-            a.bim.x = fmaf(g.y, Pv.x, a.bim.x); a.bim.y = fmaf(g.y, Pv.y, a.bim.y);
-            a.bim.z = fmaf(g.y, Pv.z, a.bim.z); a.bim.w = fmaf(g.y, Pv.w, a.bim.w);
-            if (ROT) {
-              const float4 Q = src[2 * xq + c4];
-              a.bre.x = fmaf(-g.y, Q.x, a.bre.x); a.bre.y = fmaf(-g.y, Q.y, a.bre.y);
-              a.bre.z = fmaf(-g.y, Q.z, a.bre.z); a.bre.w = fmaf(-g.y, Q.w, a.bre.w);
-              a.bim.x = fmaf(g.x, Q.x, a.bim.x); a.bim.y = fmaf(g.x, Q.y, a.bim.y);
-              a.bim.z = fmaf(g.x, Q.z, a.bim.z); a.bim.w = fmaf(g.x, Q.w, a.bim.w);
-            }
-          }
-        }
-        float4 o;
-        o.x = feat_tanh(fmaf(a.gX.x, a.bre.x, a.gY.x * a.bim.x));
-        o.y = feat_tanh(fmaf(a.gX.y, a.bre.y, a.gY.y * a.bim.y));
-        o.z = feat_tanh(fmaf(a.gX.z, a.bre.z, a.gY.z * a.bim.z));
-        o.w = feat_tanh(fmaf(a.gX.w, a.bre.w, a.gY.w * a.bim.w));
-        *reinterpret_cast<float4*>(feat + cur.row * C + c4 * 4) = o;
-      }
-      cur = nxt;
-    }
-    __syncwarp();
-    if (lane == 0) tc::mbar_arrive(empty + 8 * b);               // this warp is done reading buffer b
-  }
-}
-
 // U[v] = [dd*Bre | dd*Bim | dd*gX | dd*gY],  dd = dfeat * (1 - feat^2)
-// Tuned variant for the common case (C/4) % 32 == 0 (one float4 per lane per 128 channels) and rows of <= 32
-// entries: the row's (col, gx, gy) triples are fetched once, coalesced, one per lane, and broadcast with
-// shuffles, so the neighbour-row gathers no longer wait on dependent index loads; NB neighbours are gathered
-// per batch (3*NB independent 16-byte loads in flight per lane).
-template <bool ROT, int NB>
-__global__ void __launch_bounds__(256) spmm_features_v2_kernel(const int32_t* __restrict__ rowptr,
-                                                               const int32_t* __restrict__ colidx,
-                                                               const float2* __restrict__ vals,
-                                                               const float* __restrict__ xd,
-                                                               const float* __restrict__ pq, int ld_pq, int64_t V,
-                                                               int C, float* __restrict__ feat) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= V) return;
-  const int s = __ldg(rowptr + row), ntot = __ldg(rowptr + row + 1) - s;
-  for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
-    float4 gX = make_float4(0.f, 0.f, 0.f, 0.f), gY = gX, bre = gX, bim = gX;
-    for (int base = 0; base < ntot; base += 32) {          // rows longer than a warp: 32 entries at a time
-      const int n = (ntot - base) < 32 ? (ntot - base) : 32;
-      int mycol = 0;
-      float2 myg = make_float2(0.f, 0.f);
-      if (lane < n) {
-        mycol = __ldg(colidx + s + base + lane);
-        myg = __ldg(vals + s + base + lane);
-      }
-      for (int p0 = 0; p0 < n; p0 += NB) {
-        float4 x[NB], P[NB], Q[NB];
-        float gx[NB], gy[NB];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          const int pj = (p0 + j < n) ? p0 + j : p0;     // clamp: duplicates get weight 0
-          const int64_t col = __shfl_sync(0xffffffffu, mycol, pj);
-          const float wx = __shfl_sync(0xffffffffu, myg.x, pj), wy = __shfl_sync(0xffffffffu, myg.y, pj);
-          gx[j] = (p0 + j < n) ? wx : 0.f;
-          gy[j] = (p0 + j < n) ? wy : 0.f;
-          x[j] = ldg4(xd + col * C + c4 * 4);
-          P[j] = ldg4(pq + col * ld_pq + c4 * 4);
-          if (ROT) Q[j] = ldg4(pq + col * ld_pq + C + c4 * 4);
-        }
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          gX.x = fmaf(gx[j], x[j].x, gX.x); gX.y = fmaf(gx[j], x[j].y, gX.y);
-          gX.z = fmaf(gx[j], x[j].z, gX.z); gX.w = fmaf(gx[j], x[j].w, gX.w);
-          gY.x = fmaf(gy[j], x[j].x, gY.x); gY.y = fmaf(gy[j], x[j].y, gY.y);
-          gY.z = fmaf(gy[j], x[j].z, gY.z); gY.w = fmaf(gy[j], x[j].w, gY.w);
-          bre.x = fmaf(gx[j], P[j].x, bre.x); bre.y = fmaf(gx[j], P[j].y, bre.y);
-          bre.z = fmaf(gx[j], P[j].z, bre.z); bre.w = fmaf(gx[j], P[j].w, bre.w);
-          bim.x = fmaf(gy[j], P[j].x, bim.x); bim.y = fmaf(gy[j], P[j].y, bim.y);
-          bim.z = fmaf(gy[j], P[j].z, bim.z); bim.w = fmaf(gy[j], P[j].w, bim.w);
-          if (ROT) {
-            bre.x = fmaf(-gy[j], Q[j].x, bre.x); bre.y = fmaf(-gy[j], Q[j].y, bre.y);
-            bre.z = fmaf(-gy[j], Q[j].z, bre.z); bre.w = fmaf(-gy[j], Q[j].w, bre.w);
-            bim.x = fmaf(gx[j], Q[j].x, bim.x); bim.y = fmaf(gx[j], Q[j].y, bim.y);
-            bim.z = fmaf(gx[j], Q[j].z, bim.z); bim.w = fmaf(gx[j], Q[j].w, bim.w);
-          }
-        }
-      }
-    }
-    float4 o;
-    o.x = feat_tanh(fmaf(gX.x, bre.x, gY.x * bim.x));
-    o.y = feat_tanh(fmaf(gX.y, bre.y, gY.y * bim.y));
-    o.z = feat_tanh(fmaf(gX.z, bre.z, gY.z * bim.z));
-    o.w = feat_tanh(fmaf(gX.w, bre.w, gY.w * bim.w));
-    *reinterpret_cast<float4*>(feat + row * C + c4 * 4) = o;
-  }
-}
-
 template <bool ROT>
 __global__ void __launch_bounds__(256) features_bwd_local_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const float2* __restrict__ vals,
@@ -1056,31 +857,6 @@ int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int 
     const dn_patches& P = *g->patches;
     const int ld = rotations ? 2 * C : C;
     const size_t smem = (size_t)P.max_src * (size_t)(C + ld) * 4;
-    static int patch_v = -1;
-    if (patch_v < 0) {
-      const char* e = getenv("DN_SPMM_PATCH_V");
-      patch_v = e ? atoi(e) : 2;
-    }
-    if (patch_v == 3 && 2 * smem + 64 <= 227 * 1024) {     // experimental: copy/gather overlapped (see the kernel)
-      const size_t smem3 = 2 * smem + 64;
-      static size_t attr3[2] = {0, 0};
-      if (smem3 > attr3[rotations ? 1 : 0]) {
-        DN_CUDA_TRY(rotations ? cudaFuncSetAttribute(spmm_features_patch_async_kernel<true>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)
-                              : cudaFuncSetAttribute(spmm_features_patch_async_kernel<false>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        attr3[rotations ? 1 : 0] = smem3;
-      }
-      int dev = 0, nsm = 148;
-      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-      const unsigned grid = (unsigned)(P.n_patches < nsm ? P.n_patches : nsm);
-      if (rotations)
-        spmm_features_patch_async_kernel<true><<<grid, PA_THREADS, smem3, st>>>(P, xd, pq, ld, C, P.max_src, feat);
-      else
-        spmm_features_patch_async_kernel<false><<<grid, PA_THREADS, smem3, st>>>(P, xd, pq, ld, C, P.max_src, feat);
-      DN_LAUNCH_CHECK();
-      return DN_OK;
-    }
     if (smem <= 227 * 1024) {
       static size_t attr_set[2] = {0, 0};
       if (smem > attr_set[rotations ? 1 : 0]) {
@@ -1097,48 +873,18 @@ int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int 
     }
   }
   const float2* vals = reinterpret_cast<const float2*>(g->vals);
-  static int use_pipe = -1;
-  if (use_pipe < 0) {
-    const char* e = getenv("DN_SPMM_PIPE");
-    use_pipe = e ? atoi(e) : 0;   // measured (tools/ab_gather.py): 243-261 us vs 181 us for the warp-per-row kernel: opt-in until understood
+  static int use_blk = -1;
+  if (use_blk < 0) {
+    const char* e = getenv("DN_SPMM_BLK");
+    use_blk = e ? atoi(e) : 1;   // measured (tools/ab_gather.py, V=200k): 1 -> 174 us (282 permuted) vs 181 (347) for the warp-per-row kernel
   }
-  if (C == 128 && use_pipe) {
-    int dev = 0, nsm = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t nblk = (V + GP_ROWS - 1) / GP_ROWS;
+  if (C == 128 && use_blk) {
+    const unsigned ctas = (unsigned)((V + GB_ROWS - 1) / GB_ROWS);
     const int ld = rotations ? 2 * C : C;
-    // use_pipe: 1 = 4 neighbours per batch, 2 CTAs/SM (no spills) | 2 = 2 per batch, 4 CTAs/SM | 3 = 3 per batch, 3 CTAs/SM
-    const int minb = use_pipe == 2 ? 4 : (use_pipe == 3 ? 3 : 2);
-    int64_t ctas = (nblk + 7) / 8;
-    if (ctas > (int64_t)minb * nsm) ctas = (int64_t)minb * nsm;
-#define DN_PIPE_LAUNCH(ROT_, NB_, MB_) \
-    spmm_features_pipe_kernel<ROT_, NB_, MB_><<<(unsigned)ctas, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, feat)
-    if (rotations) {
-      if (use_pipe == 2) DN_PIPE_LAUNCH(true, 2, 4); else if (use_pipe == 3) DN_PIPE_LAUNCH(true, 3, 3); else DN_PIPE_LAUNCH(true, 4, 2);
-    } else {
-      if (use_pipe == 2) DN_PIPE_LAUNCH(false, 2, 4); else if (use_pipe == 3) DN_PIPE_LAUNCH(false, 3, 3); else DN_PIPE_LAUNCH(false, 4, 2);
-    }
-#undef DN_PIPE_LAUNCH
-    DN_LAUNCH_CHECK();
-    return DN_OK;
-  }
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("DN_SPMM_VARIANT");
-    // measured on B200 (tools/ablate_spmm.py, V=200k C=128): the kernel is L1/L2-throughput bound, so more
-    // gathers in flight per lane (variants 2,3) are slower; variant 1 wins only on permuted vertex orders
-    variant = e ? atoi(e) : 0;
-  }
-  if ((C % 128) == 0 && variant > 0) {     // one warp per row, one float4 per lane per 128 channels
-    const unsigned blocks = (unsigned)((V * 32 + 255) / 256);
-    const int ld = rotations ? 2 * C : C;
-    if (rotations) {
-      if (variant == 1) spmm_features_v2_kernel<true, 2><<<blocks, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, C, feat);
-      else if (variant == 2) spmm_features_v2_kernel<true, 4><<<blocks, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, C, feat);
-      else spmm_features_v2_kernel<true, 7><<<blocks, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, C, feat);
-    } else {
-      spmm_features_v2_kernel<false, 4><<<blocks, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, C, feat);
-    }
+    if (rotations)
+      spmm_features_blk_kernel<true, 7, 2><<<ctas, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, feat);
+    else
+      spmm_features_blk_kernel<false, 7, 2><<<ctas, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, feat);
     DN_LAUNCH_CHECK();
     return DN_OK;
   }

@@ -23,8 +23,14 @@ def from_basis(values, basis):
     return torch.matmul(basis, values)
 
 
-def block_forward(x_in, mass, evals, evecs, gradX, gradY, params, with_gradient_features=True):
-    """layers.py:200-241 for a batched input (B,V,C); gradX/gradY sparse COO (B,V,V) or lists of (V,V)."""
+def block_forward(x_in, mass, evals, evecs, gradX, gradY, params, with_gradient_features=True, relu_masks=None,
+                  pre_acts=None):
+    """layers.py:200-241 for a batched input (B,V,C); gradX/gradY sparse COO (B,V,V) or lists of (V,V).
+
+    Test hooks (not reference behaviour): ``pre_acts`` (a list) receives every hidden layer's pre-activation;
+    ``relu_masks`` (one bool tensor per hidden layer) replaces ``relu(h)`` by ``h * mask`` so that a gradient can be
+    checked under a GIVEN activation pattern -- the gradient of ReLU is discontinuous at 0, and an fp32 forward may
+    land on the other side of a kink than the fp64 one for pre-activations of order 1e-7."""
     t = torch.clamp(params["diffusion.diffusion_time"], min=1e-8)                  # layers.py:48-49
     x_spec = to_basis(x_in, evecs, mass)                                           # :59
     coefs = torch.exp(-evals.unsqueeze(-1) * t.unsqueeze(0))                       # :62-63
@@ -53,6 +59,8 @@ def block_forward(x_in, mass, evals, evecs, gradX, gradY, params, with_gradient_
         b = params["mlp.miniMLP_mlp_layer_{:03d}.bias".format(i)]
         h = torch.addmm(b, h.reshape(-1, h.shape[-1]), w.t()).reshape(h.shape[:-1] + (w.shape[0],))
         if "mlp.miniMLP_mlp_layer_{:03d}.weight".format(i + 1) in params:
-            h = torch.relu(h)
+            if pre_acts is not None:
+                pre_acts.append(h.detach())
+            h = torch.relu(h) if relu_masks is None else h * relu_masks[i].to(h.dtype).reshape(h.shape)
         i += 1
     return h + x_in                                                                # :239

@@ -1,6 +1,6 @@
 """A/B of the gradient-features gather variants inside the fused block forward (V=200k, C=128): per-stage device times
 from dn_block_fwd_profile and parity vs the exact SIMT engine; each setting in its own process (env read once).
-DN_SPMM_PIPE: 0 = round-1 warp-per-row kernel, 1/2/3 = pipelined FFMA2 kernel (4/2/3 neighbours per batch)."""
+DN_SPMM_BLK: 0 = round-1 warp-per-row kernel, 1 = block gather (64 rows per CTA, metadata staged in smem, FFMA2; default at C=128)."""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = r'''
@@ -31,8 +31,8 @@ for permute in (False, True):
             if it >= 2: acc = [a + b for a, b in zip(acc, prof)]
     print("permute={} err {:.2e} stages_us {}".format(permute, err, {n: round(100 * a, 1) for n, a in zip(dn.ops.PROFILE_STAGES, acc)}), flush=True)
 ''' % ROOT
-for v in sys.argv[1:] or ["0", "1", "2", "3"]:
-    env = dict(os.environ, DN_SPMM_PIPE=v, DN_SPMM_PATCH="0")
+for v in sys.argv[1:] or ["0", "1"]:
+    env = dict(os.environ, DN_SPMM_BLK=v, DN_SPMM_PATCH="0")
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=400)
     out = "\n".join(l for l in r.stdout.splitlines() if l.startswith("permute"))
-    print("DN_SPMM_PIPE={}:\n{}".format(v, out or r.stderr.strip()[-800:]), flush=True)
+    print("DN_SPMM_BLK={}:\n{}".format(v, out or r.stderr.strip()[-800:]), flush=True)
