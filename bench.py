@@ -402,6 +402,71 @@ def run_aux(args, rank, world, local):
                                 "allreduce": "one flat fp32 buffer of {} floats, NCCL".format(nparam),
                                 "allreduce_ms_median": ar[len(ar) // 2], "allreduce_ms_max": ar[-1]},
                      "gpu_launches": launches})
+    elif args.workload == "config3":
+        # config 3: large-mesh inference, V = 200k, K = 128, C_width = 256, 4 blocks, bf16 arithmetic (DN_ENGINE_BF16:
+        # one bf16 tensor-core pass, fp32 accumulate; tensors stay fp32 in HBM), one mesh per GPU
+        eng = "bf16" if args.engine == "tc3x" else args.engine
+        dn.set_engine(eng)
+        C3 = 256
+        net = _seeded_net(dn, C_in, C_out, C3, NB, dev, seed=0).eval()
+        (x, y, ops_t), = _mesh_batch(dn, [(N_TORUS, M_TORUS)], K, C_in, dev, seed0=rank)
+        V = x.shape[0]
+        mass, _, evals, evecs, gX, gY = ops_t
+        gops = dn.ops.prepare_operators(gX, gY)
+        with torch.no_grad():
+            fwd = lambda: net(x, mass, L=None, evals=evals, evecs=evecs, gradX=gops, gradY=None)
+            ms, launches = timed(fwd)
+            # one block alone, with the per-stage device times of dn_block_fwd_profile
+            blk = net.blocks[1]
+            xb = torch.randn(V, C3, device=dev)
+            A_re, A_im = blk.gradient_features.weights()
+            lins = blk.mlp.linears()
+            run = lambda prof=None: dn.ops.block_forward_raw(xb, mass, evals, evecs, gops, blk.diffusion.diffusion_time, A_re,
+                                                             A_im, [l.weight for l in lins], [l.bias for l in lins], True,
+                                                             profile=prof)
+            acc = [0.0] * len(dn.ops.PROFILE_STAGES)
+            for it in range(8):
+                prof = []
+                run(prof)
+                if it >= 2:
+                    acc = [a + b for a, b in zip(acc, prof)]
+            stages = {k + "_ms": a / 6 for k, a in zip(dn.ops.PROFILE_STAGES, acc)}
+            blk_ms, _ = timed(run)
+        pk = peaks()
+        mlp_flops = 2.0 * V * (3 * C3 * C3 + 2 * C3 * C3)
+        mlp_ms = stages["mlp_ms"]
+        blk_flops = V * flops_per_vertex(K, C3)
+        blk_bytes = V * bytes_per_vertex(K, C3)
+        gpu_base = None
+        if rank == 0 and world == 1:
+            try:
+                prev = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = False
+                rnet = _reference_net(net.state_dict(), C_in, C_out, C3, NB, dev)
+                if rnet is not None:
+                    rnet.eval()
+                    with torch.no_grad():
+                        rf = lambda: rnet(x, mass, L=None, evals=evals, evecs=evecs, gradX=gX, gradY=gY)
+                        rms, _ = timed(rf)
+                        err = float((fwd() - rf()).abs().max() / rf().abs().max())
+                    gpu_base = {"value": V / (rms * 1e-3) / 1e6, "unit": "Mverts/s", "ms_per_step": rms, "kind": "reference",
+                                "how": "reference DiffusionNet (4 x 256), torch eager on this B200, fp32 (TF32 off)",
+                                "speedup_ours": rms / ms, "max_rel_diff_vs_ours": err}
+                torch.backends.cuda.matmul.allow_tf32 = prev
+            except Exception as exc:
+                gpu_base = {"unavailable": repr(exc)[:200]}
+        line.update({"metric": "DiffusionNet (4 blocks, C_width=256) forward Mverts/sec at V=200k,K=128, bf16 arithmetic",
+                     "value": world * V / (ms * 1e-3) / 1e6, "ms_per_step": ms, "scaling": "weak", "dtype": "bf16 (fp32 accumulate, fp32 tensors in HBM)",
+                     "config": {"workload": "config3 net_fwd V={} K=128 C=256 4 blocks, 1 mesh per GPU".format(V), "engine": eng,
+                                "block_ms": blk_ms, "block_stages_ms": stages},
+                     "roofline": {"bound": "tensor", "kernel": "rows_chain16_kernel (MiniMLP 768-256-256-256 + skip)",
+                                  "achieved": mlp_flops / (mlp_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
+                                  "unit": "TFLOP/s", "frac": mlp_flops / (mlp_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                                  "hbm_frac": 4.0 * V * C3 * 4 / (mlp_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                  "block_tflops": blk_flops / (blk_ms * 1e-3) / 1e12,
+                                  "block_hbm_frac_fp32_bytes": blk_bytes / (blk_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                  "peak_source": pk["source"], "traffic": None},
+                     "gpu_launches": launches, "gpu_baseline": gpu_base})
     else:
         # config 4: 32 small meshes (V ~ 2k), 4-block net forward, meshes sharded over the ranks, CUDA-graph replay
         n_global = 32
@@ -412,14 +477,27 @@ def run_aux(args, rank, world, local):
         meshes = _mesh_batch(dn, shapes, K, C_in, dev, seed0=0)
         items = [dict(x_in=meshes[i][0], mass=meshes[i][2][0], evals=meshes[i][2][2], evecs=meshes[i][2][3],
                       gradX=meshes[i][2][4], gradY=meshes[i][2][5]) for i in mine]
-        gn = dn.graphs.GraphedNet(net, n_streams=4)
+        # (a) one launch sequence over the whole shard: MeshBatch (one vertex range, block-diagonal CSR, per-mesh
+        #     spectral weights picked per tile) -> 5-6 launches per block whatever the number of meshes
+        mb = dn.MeshBatch([dict(mass=it["mass"], evals=it["evals"], evecs=it["evecs"], gradX=it["gradX"], gradY=it["gradY"])
+                           for it in items])
+        x_cat = mb.pack([it["x_in"] for it in items])
         with torch.no_grad():
-            ms, launches = timed(lambda: gn.forward_batch(items))
+            ms, launches = timed(lambda: net.forward_batch(mb, x_cat))
+            # (b) round 1's route for comparison: per-mesh launches replayed from CUDA graphs on 4 streams
+            gn = dn.graphs.GraphedNet(net, n_streams=4)
+            ms_graphs, _ = timed(lambda: gn.forward_batch(items))
+            outs = net.forward_batch(mb, x_cat)
+            refs = gn.forward_batch(items)
+            err = max(float((o - r).abs().max() / r.abs().max()) for o, r in zip(outs, refs))
         Vtot = sum(a * b for a, b in shapes)
         line.update({"metric": "DiffusionNet (4 blocks) forward over a batch of 32 small meshes, Mverts/sec",
                      "value": Vtot / (ms * 1e-3) / 1e6, "ms_per_step": ms, "scaling": "strong",
                      "config": {"workload": "small_batch 32 meshes V~2k K=128 C=128 4 blocks, sharded x{}".format(world),
-                                "engine": args.engine, "meshes_per_rank": len(mine), "replay": "CUDA graphs, 4 streams"},
+                                "engine": args.engine, "meshes_per_rank": len(mine),
+                                "route": "MeshBatch: one batched launch per stage (dn_block_fwd_batched)",
+                                "padded_rows": mb.V, "per_mesh_cuda_graphs_ms": ms_graphs,
+                                "max_rel_diff_vs_per_mesh": err},
                      "gpu_launches": launches})
     if rank == 0:
         print(json.dumps(line))
@@ -437,8 +515,8 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("DN_B200_ENGINE", "tc3x"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=8)
-    ap.add_argument("--workload", default="block_fwd", choices=["block_fwd", "fwd_bwd", "train", "small_batch"],
-                    help="block_fwd = the BASELINE metric (default); the others are BASELINE configs 2 / 5 / 4")
+    ap.add_argument("--workload", default="block_fwd", choices=["block_fwd", "fwd_bwd", "train", "small_batch", "config3"],
+                    help="block_fwd = the BASELINE metric (default); the others are BASELINE configs 2 / 5 / 4 / 3")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -633,7 +711,11 @@ def main():
         tf32 = measure_tf32_peak(dev)
         C, K = C_WIDTH, K_EIG
         nnz = NNZ_ROW * V
-        passes = 3 if args.engine == "tc3x" else 1
+        # tensor-pipe work per fp32 product in TF32-pass equivalents: the default tc3x chain issues, per 32-wide K-stage,
+        # 4 kind::tf32 MMAs (hi*hi) + 4 kind::f16 bf16 MMAs (K = 16: both correction terms) = 8 MMA slots where plain
+        # 3xTF32 needs 12 -> 2 equivalents (DN_TC_HYBRID=0 restores 3); bf16 engine: half a TF32 pass
+        hybrid = os.environ.get("DN_TC_HYBRID", "1") != "0"
+        passes = {"tc3x": 2.0 if hybrid else 3.0, "tc1x": 1.0, "bf16": 0.5}.get(args.engine, 3.0)
         # algorithmic (minimum) HBM bytes and useful fp32 flops per launch of each kernel
         work = {
             "to_basis": (4 * V * (K + C) + 4 * V, 2 * K * C * V, "to_basis_kernel (split-V tcgen05)"),
@@ -670,8 +752,9 @@ def main():
         if dom["bound"] == "tensor":
             roof = {"bound": "tensor", "achieved": dom["issued_tf32_tflops"], "peak": tf32["tf32_tflops"],
                     "unit": "TFLOP/s", "frac": dom["tf32_frac"],
-                    "note": "kind::tf32 MMAs issued (3 per fp32 product in 3xTF32 mode) over the cuBLAS TF32 GEMM rate "
-                            "measured in this run (burst); useful fp32 flops are a third of `achieved`"}
+                    "note": "tensor-pipe work issued, in TF32-pass equivalents (tc3x: TF32 hi*hi + bf16 correction MMAs = 2 "
+                            "per fp32 product), over the cuBLAS TF32 GEMM rate measured in this run (burst); useful fp32 "
+                            "flops are `achieved` / passes_equiv", "passes_equiv": passes}
         else:
             roof = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": dom["hbm_frac"],

@@ -14,13 +14,13 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdiffusion_net_b200.so")
-SOURCES = ["dn_simt.cu", "dn_geom.cu", "dn_tc.cu", "dn_chain.cu", "dn_capi.cu"]
+SOURCES = ["dn_simt.cu", "dn_geom.cu", "dn_tc.cu", "dn_chain.cu", "dn_chain16.cu", "dn_capi.cu"]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "diffusion_net_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
-ENGINE_SIMT, ENGINE_TC3X, ENGINE_TC1X = 0, 1, 2
+ENGINE_SIMT, ENGINE_TC3X, ENGINE_TC1X, ENGINE_BF16 = 0, 1, 2, 3
 
 
 def _stale() -> bool:
@@ -63,6 +63,11 @@ class dn_block_params(C.Structure):
                 ("mlp_bias_host", C.POINTER(C.c_void_p)), ("mlp_dims_host", C.POINTER(C.c_int))]
 
 
+class dn_mesh_batch(C.Structure):
+    _fields_ = [("n_meshes", C.c_int32), ("n_tb_ctas", C.c_int32), ("tile_mesh", C.c_void_p), ("tb_rows", C.c_void_p),
+                ("mesh_cta_begin", C.c_void_p)]
+
+
 _P, _I, _L = C.c_void_p, C.c_int, C.c_int64
 _PP = C.POINTER(C.c_void_p)
 _IP = C.POINTER(C.c_int)
@@ -93,6 +98,9 @@ SIGNATURES = {
                           _I, _P]),
     "dn_block_fwd_profile": (_I, [_P, _P, _P, _P, C.POINTER(dn_csr), C.POINTER(dn_block_params), _L, _I, _I, _P, _P, _L,
                                   _I, _P, C.POINTER(C.c_float)]),
+    "dn_mesh_batch_plan": (_I, [_I, _P, _I, _P, _P, _P, _P]),
+    "dn_block_fwd_batched": (_I, [_P, _P, _P, _P, C.POINTER(dn_csr), C.POINTER(dn_block_params), C.POINTER(dn_mesh_batch),
+                                  _L, _I, _I, _P, _P, _L, _I, _P]),
 }
 
 _lib = None
@@ -113,7 +121,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.dn_abi_version() != 3:
+    if lib.dn_abi_version() != 4:
         raise RuntimeError("diffusion_net_b200: ABI version mismatch")
     _lib = lib
     return lib

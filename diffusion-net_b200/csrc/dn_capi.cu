@@ -22,8 +22,8 @@ struct Bump {
 
 constexpr int64_t kPartialFloats = 16ll << 20;  // 64 MiB split-V partial sums
 
-inline bool use_tc(int engine) { return engine == DN_ENGINE_TC3X || engine == DN_ENGINE_TC1X; }
-inline int tc_passes(int engine) { return engine == DN_ENGINE_TC1X ? 1 : 3; }
+inline bool use_tc(int engine) { return engine == DN_ENGINE_TC3X || engine == DN_ENGINE_TC1X || engine == DN_ENGINE_BF16; }
+inline int tc_passes(int engine) { return engine == DN_ENGINE_TC1X ? 1 : (engine == DN_ENGINE_BF16 ? DN_PASSES_BF16 : 3); }
 
 inline DnLayer make_layer(const float* W, int64_t ldw, int w_trans, const float* bias, int relu, int K, int N,
                           float* out, int64_t ld_out) {
@@ -46,7 +46,7 @@ inline DnRowsSrc one_src(const float* p, int width, int64_t ld) {
 int run_chain(const DnRowsSrc& src, DnLayer* layers, int n_layers, int64_t V, int engine, float* tmp0,
               float* tmp1, void* tc_ws, int64_t tc_ws_bytes, cudaStream_t st) {
   const bool tc = use_tc(engine) && tc_supported_device();
-  if (tc && tc_rows_chain_supported(src, layers, n_layers) == DN_OK) {
+  if (tc && tc_rows_chain_supported(src, layers, n_layers, tc_passes(engine)) == DN_OK) {
     return tc_rows_chain(src, layers, n_layers, V, tc_passes(engine), tc_ws, tc_ws_bytes, st);
   }
   // not fusable as a whole (e.g. a 256-wide layer inside a chain): layer by layer, each on the
@@ -63,7 +63,7 @@ int run_chain(const DnRowsSrc& src, DnLayer* layers, int n_layers, int64_t V, in
     }
     L.out = o; L.ld_out = ldo;
     int rc;
-    if (tc && tc_rows_chain_supported(cur, &L, 1) == DN_OK)
+    if (tc && tc_rows_chain_supported(cur, &L, 1, tc_passes(engine)) == DN_OK)
       rc = tc_rows_chain(cur, &L, 1, V, tc_passes(engine), tc_ws, tc_ws_bytes, st);
     else
       rc = simt_rows_gemm(cur, L, V, st);
@@ -78,6 +78,15 @@ int to_basis_partials(const float* values, const float* basis, const float* mass
   if (use_tc(engine) && tc_supported_device() && tc_to_basis_supported(K, C) == DN_OK &&
       (int64_t)148 * K * C <= partial_floats) {
     return tc_to_basis_partial(values, basis, massvec, V, K, C, partial, P, tc_passes(engine), st);
+  }
+  // wider than one accumulator set (C_width = 256): 128-column slices, each its own launch into the shared partials
+  if (use_tc(engine) && tc_supported_device() && C > 128 && C % 128 == 0 && tc_to_basis_supported(K, 128) == DN_OK &&
+      (int64_t)148 * K * C <= partial_floats) {
+    for (int c0 = 0; c0 < C; c0 += 128) {
+      const int rc = tc_to_basis_partial(values + c0, basis, massvec, V, K, 128, partial + c0, P, tc_passes(engine), st, C, C);
+      if (rc) return rc;
+    }
+    return DN_OK;
   }
   // out[k][c] = sum_v basis[v][k] * (mass[v] * values[v][c])
   return simt_atb_partial_st(basis, K, K, values, C, C, massvec, V, partial, partial_floats, P, st);
@@ -100,7 +109,7 @@ int atb(const float* A, int64_t lda, int I, const float* B, int64_t ldb, int J, 
 
 // one dense layer on the tensor-core chain kernel when it takes the shape, else the exact SIMT kernel
 int one_layer(const DnRowsSrc& src, DnLayer& L, int64_t V, int engine, void* tc_ws, int64_t tc_ws_bytes, cudaStream_t st) {
-  if (use_tc(engine) && tc_supported_device() && tc_rows_chain_supported(src, &L, 1) == DN_OK)
+  if (use_tc(engine) && tc_supported_device() && tc_rows_chain_supported(src, &L, 1, tc_passes(engine)) == DN_OK)
     return tc_rows_chain(src, &L, 1, V, tc_passes(engine), tc_ws, tc_ws_bytes, st);
   return simt_rows_gemm(src, L, V, st);
 }
@@ -409,7 +418,7 @@ int dn_gradient_features_bwd(const dn_csr* grad, const dn_csr* grad_t, const flo
     DnLayer L = make_layer(A_re, C, /*w_trans=*/1, nullptr, 0, rot ? 2 * C : C, C, grad_x, C);
     if (rot) { L.W2 = A_im; L.n_split = C; }
     L.residual = dxd; L.ld_res = C;
-    if (use_tc(engine) && tc_supported_device() && tc_rows_chain_supported(s, &L, 1) == DN_OK) {
+    if (use_tc(engine) && tc_supported_device() && tc_rows_chain_supported(s, &L, 1, tc_passes(engine)) == DN_OK) {
       if ((rc = tc_rows_chain(s, &L, 1, V, tc_passes(engine), tcws, tcws_bytes, st))) return rc;
     } else {                                       // exact SIMT route: one source at a time
       DnRowsSrc s0 = one_src(dP, C, C);
@@ -463,7 +472,7 @@ int dn_mini_mlp_fwd(const float* const* src_host, const int* src_width_host, int
   }
   Bump ws(workspace, ws_bytes);
   float *t0 = nullptr, *t1 = nullptr;
-  const bool fused = use_tc(engine) && tc_supported_device() && tc_rows_chain_supported(src, layers, n_layers) == DN_OK;
+  const bool fused = use_tc(engine) && tc_supported_device() && tc_rows_chain_supported(src, layers, n_layers, tc_passes(engine)) == DN_OK;
   if (!fused && n_layers > 1) {
     t0 = ws.take(V * maxn);
     t1 = ws.take(V * maxn);
@@ -538,7 +547,8 @@ int dn_mini_mlp_bwd(const float* grad_out, const float* const* src_host, const i
 
 static int block_fwd_impl(const float* x_in, const float* mass, const float* evals, const float* evecs,
                           const dn_csr* grad, const dn_block_params* p, int64_t V, int K, int C, float* out,
-                          void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream, cudaEvent_t* ev) {
+                          void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream, cudaEvent_t* ev,
+                          const dn_mesh_batch* batch = nullptr) {
   // ev (optional, DN_PROFILE_STAGES + 1 events): recorded on the launching stream between the stages
   auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], (cudaStream_t)stream); };
   if (!x_in || !mass || !evals || !evecs || !p || !p->diffusion_time || !out || V < 0 || K <= 0 || C <= 0)
@@ -562,19 +572,45 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
   int rc, P = 0;
   mark(0);
   // (a1) spectral diffusion: to_basis -> exp(-lambda t) -> from_basis   [layers.py:56-67]
-  if ((rc = to_basis_partials(x_in, evecs, mass, V, K, C, partial, pf, &P, engine, st))) return rc;
+  if (batch) {
+    // grouped split-V: every CTA reduces a row range inside one mesh
+    if (!use_tc(engine) || !tc_supported_device() || (V % 128) || batch->n_meshes < 1 || !batch->tile_mesh ||
+        !batch->tb_rows || !batch->mesh_cta_begin || batch->n_tb_ctas < 1 || (int64_t)batch->n_tb_ctas * K * C > pf)
+      return DN_ERR_UNSUPPORTED;
+    if (tc_to_basis_supported(K, C) == DN_OK) {
+      if ((rc = tc_to_basis_partial(x_in, evecs, mass, V, K, C, partial, &P, tc_passes(engine), st, 0, 0, batch->tb_rows,
+                                    batch->n_tb_ctas)))
+        return rc;
+    } else if (C > 128 && C % 128 == 0 && tc_to_basis_supported(K, 128) == DN_OK) {
+      for (int c0 = 0; c0 < C; c0 += 128)
+        if ((rc = tc_to_basis_partial(x_in + c0, evecs, mass, V, K, 128, partial + c0, &P, tc_passes(engine), st, C, C,
+                                      batch->tb_rows, batch->n_tb_ctas)))
+          return rc;
+    } else {
+      return DN_ERR_UNSUPPORTED;
+    }
+  } else if ((rc = to_basis_partials(x_in, evecs, mass, V, K, C, partial, pf, &P, engine, st))) {
+    return rc;
+  }
   mark(1);
 
   // every dense layer of the block: [0] from_basis, [1] (a5, commuted) [P|Q] = x_diffuse [A_re;A_im]^T,
   // [2..] cat -> MiniMLP -> + x_in  [layers.py:229-239]
   const int nm = p->n_mlp_layers;
-  DnLayer L[2 + DN_MAX_LAYERS];
+  DnLayer L[3 + DN_MAX_LAYERS];
   L[0] = make_layer(S, C, 1, nullptr, 0, K, C, xd, C);
   int nfront = 1;
   if (p->with_gradient_features) {
-    L[1] = make_layer(p->A_re, C, 0, nullptr, 0, C, npq, pq, npq);
-    if (rot) { L[1].W2 = p->A_im; L[1].n_split = C; }
-    nfront = 2;
+    if (rot && npq > 256) {
+      // [P|Q] wider than one tensor-core layer (C_width = 256): P and Q are separate layers writing the two halves
+      L[1] = make_layer(p->A_re, C, 0, nullptr, 0, C, C, pq, npq);
+      L[2] = make_layer(p->A_im, C, 0, nullptr, 0, C, C, pq + C, npq);
+      nfront = 3;
+    } else {
+      L[1] = make_layer(p->A_re, C, 0, nullptr, 0, C, npq, pq, npq);
+      if (rot) { L[1].W2 = p->A_im; L[1].n_split = C; }
+      nfront = 2;
+    }
   }
   const int nsrc = p->with_gradient_features ? 3 : 2;
   if (p->mlp_dims_host[0] != nsrc * C) return DN_ERR_INVALID_ARGUMENT;
@@ -598,21 +634,46 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
   src_mlp.nsrc = nsrc;
   // one launch packs (hi/lo split + UMMA layout) every weight the tensor-core kernels will stream
   const bool tc = use_tc(engine) && tc_supported_device();
-  const bool tc_front = tc && ((nfront == 2 && tc_rows_chain_supported(src_fb, &L[0], 2) == DN_OK) ||
-                               (tc_rows_chain_supported(src_fb, &L[0], 1) == DN_OK &&
-                                (nfront == 1 || tc_rows_chain_supported(src_pq, &L[1], 1) == DN_OK)));
-  const bool tc_mlp = tc && tc_rows_chain_supported(src_mlp, &L[nfront], nm) == DN_OK;
+  const int passes = tc_passes(engine);
+  const bool front_fused = tc && nfront == 2 && tc_rows_chain_supported(src_fb, &L[0], 2, passes) == DN_OK;
+  bool tc_front = front_fused;
+  if (tc && !front_fused) {
+    tc_front = tc_rows_chain_supported(src_fb, &L[0], 1, passes) == DN_OK;
+    for (int l = 1; l < nfront; ++l) tc_front = tc_front && tc_rows_chain_supported(src_pq, &L[l], 1, passes) == DN_OK;
+  }
+  const bool tc_mlp = tc && tc_rows_chain_supported(src_mlp, &L[nfront], nm, passes) == DN_OK;
   // the spectral multiplier S = exp(-lambda t) * (reduced partial sums) is layer 0's weight: when the tensor-core path
   // takes the front chain it is formed inside the pack launch (no separate scale kernel, S never round-trips HBM)
+  if (batch && !tc_front) return DN_ERR_UNSUPPORTED;
   if (!tc_front)
     if ((rc = launch_spectral_scale(partial, P, evals, p->diffusion_time, K, C, nullptr, S, 1, st))) return rc;
   mark(2);
   if (tc_front) {
-    if (nfront == 2 && tc_rows_chain_supported(src_fb, &L[0], 2) == DN_OK) tc_choose_pack_fmt(src_fb, &L[0], 2);
-    else { tc_choose_pack_fmt(src_fb, &L[0], 1); if (nfront == 2) tc_choose_pack_fmt(src_pq, &L[1], 1); }
+    if (front_fused) tc_choose_pack_fmt(src_fb, &L[0], 2, passes);
+    else {
+      tc_choose_pack_fmt(src_fb, &L[0], 1, passes);
+      for (int l = 1; l < nfront; ++l) tc_choose_pack_fmt(src_pq, &L[l], 1, passes);
+    }
   }
-  if (tc_mlp) tc_choose_pack_fmt(src_mlp, &L[nfront], nm);
-  if (tc_front || tc_mlp) {
+  if (tc_mlp) tc_choose_pack_fmt(src_mlp, &L[nfront], nm, passes);
+  if (batch) {
+    // one packed spectral multiplier per mesh (layer 0 of the front chain picks its matrix per tile), then every other
+    // weight of the block in one more launch
+    const int64_t pb0 = tc_chain_ws_bytes(&L[0], 1) * batch->n_meshes;
+    float* pk0 = ws.take(pb0 / 4);
+    if (!pk0) return DN_ERR_WORKSPACE;
+    if ((rc = tc_pack_spectral_batched(&L[0], batch->n_meshes, pk0, pb0, partial, batch->mesh_cta_begin, evals,
+                                       p->diffusion_time, 1, batch->tile_mesh, st)))
+      return rc;
+    const int cnt = (nfront - 1) + (tc_mlp ? nm : 0);
+    if (cnt > 0) {
+      DnLayer* first = (nfront > 1) ? &L[1] : &L[nfront];
+      const int64_t pb = tc_chain_ws_bytes(first, cnt);
+      float* pk = ws.take(pb / 4);
+      if (!pk) return DN_ERR_WORKSPACE;
+      if ((rc = tc_pack_layers(first, cnt, pk, pb, st))) return rc;
+    }
+  } else if (tc_front || tc_mlp) {
     DnLayer* first = tc_front ? &L[0] : &L[nfront];
     const int cnt = (tc_front ? nfront : 0) + (tc_mlp ? nm : 0);
     const int64_t pb = tc_chain_ws_bytes(first, cnt);
@@ -631,13 +692,13 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
   }
   void* tcws = ws.base + ws.off;
   const int64_t tcws_bytes = ws.size - ws.off;
-  // from_basis and [P|Q]: one fused two-layer chain on the TMEM-A kernel when it fits, else two launches
-  if (nfront == 2 && tc && tc_rows_chain_supported(src_fb, &L[0], 2) == DN_OK) {
+  // from_basis and [P|Q]: one fused two-layer chain when it fits, else one launch per layer
+  if (front_fused) {
     if ((rc = run_chain(src_fb, &L[0], 2, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
   } else {
     if ((rc = run_chain(src_fb, &L[0], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
-    if (nfront == 2)
-      if ((rc = run_chain(src_pq, &L[1], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
+    for (int l = 1; l < nfront; ++l)
+      if ((rc = run_chain(src_pq, &L[l], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
   }
   mark(4);
   // (a4+a5) sparse tangent gradient + complex inner product + tanh   [layers.py:216-226,128-130]
@@ -653,6 +714,56 @@ int dn_block_fwd(const float* x_in, const float* mass, const float* evals, const
                  const dn_block_params* p, int64_t V, int K, int C, float* out, void* workspace, int64_t ws_bytes,
                  int engine, dn_stream_t stream) {
   return block_fwd_impl(x_in, mass, evals, evecs, grad, p, V, K, C, out, workspace, ws_bytes, engine, stream, nullptr);
+}
+
+int dn_block_fwd_batched(const float* x_in, const float* mass, const float* evals, const float* evecs, const dn_csr* grad,
+                         const dn_block_params* p, const dn_mesh_batch* batch, int64_t V, int K, int C, float* out,
+                         void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream) {
+  if (!batch) return DN_ERR_INVALID_ARGUMENT;
+  return block_fwd_impl(x_in, mass, evals, evecs, grad, p, V, K, C, out, workspace, ws_bytes, engine, stream, nullptr, batch);
+}
+
+int dn_mesh_batch_plan(int n_meshes, const int32_t* n_rows_host, int sm_count, int32_t* row_begin_host,
+                       int32_t* tile_mesh_host, int32_t* tb_rows_host, int32_t* mesh_cta_begin_host) {
+  if (n_meshes < 1 || !n_rows_host || !row_begin_host || !tile_mesh_host || !tb_rows_host || !mesh_cta_begin_host)
+    return DN_ERR_INVALID_ARGUMENT;
+  if (sm_count < 1) sm_count = 148;
+  int64_t row = 0, chunks_total = 0;
+  for (int b = 0; b < n_meshes; ++b) {
+    if (n_rows_host[b] < 0) return DN_ERR_INVALID_ARGUMENT;
+    row_begin_host[b] = (int32_t)row;
+    const int64_t padded = ((int64_t)n_rows_host[b] + 127) / 128 * 128;
+    for (int64_t t = row / 128; t < (row + padded) / 128; ++t) tile_mesh_host[t] = b;
+    row += padded;
+    if (row >= (1ll << 31) - 256) return DN_ERR_UNSUPPORTED;
+    chunks_total += ((int64_t)n_rows_host[b] + 15) / 16;
+  }
+  row_begin_host[n_meshes] = (int32_t)row;
+  // CTAs per mesh proportional to its 16-row chunks (>= 1), about sm_count in total, at most 1024
+  int n_ctas = 0;
+  for (int b = 0; b < n_meshes; ++b) {
+    const int64_t chunks = ((int64_t)n_rows_host[b] + 15) / 16;
+    int64_t want = chunks_total > 0 ? (chunks * sm_count + chunks_total / 2) / chunks_total : 1;
+    if (want < 1) want = 1;
+    if (want > chunks && chunks > 0) want = chunks;
+    if (n_ctas + want + (n_meshes - 1 - b) > 1024) want = 1;
+    if (n_ctas + want > 1024) return DN_ERR_UNSUPPORTED;
+    mesh_cta_begin_host[b] = n_ctas;
+    const int64_t per = chunks > 0 ? (chunks + want - 1) / want : 0;
+    if (per > 0) want = (chunks + per - 1) / per;              // no empty CTAs
+    for (int64_t c = 0; c < want; ++c) {
+      int64_t rb = row_begin_host[b] + c * per * 16;
+      int64_t re = rb + per * 16;
+      const int64_t end = (int64_t)row_begin_host[b] + n_rows_host[b];
+      if (rb > end) rb = end;
+      if (re > end) re = end;
+      tb_rows_host[2 * n_ctas] = (int32_t)rb;
+      tb_rows_host[2 * n_ctas + 1] = (int32_t)re;
+      ++n_ctas;
+    }
+  }
+  mesh_cta_begin_host[n_meshes] = n_ctas;
+  return n_ctas;
 }
 
 int dn_block_fwd_profile(const float* x_in, const float* mass, const float* evals, const float* evecs,

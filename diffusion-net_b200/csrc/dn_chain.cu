@@ -75,6 +75,8 @@ struct C3Params {
   int nr_shift;    // log2(row-box slots): 2 or 1;  output staging buffers = 6 - slots
   int64_t V;
   long long* trace;   // optional (tools/trace_chain3.py): per-warp (event, clock64) pairs of CTA 0
+  const int32_t* tile_group;   // optional (mesh batches): layer 0 of tile t streams the packed matrix number tile_group[t]
+  int64_t group_stride;        //   (floats between the per-mesh matrices)
 };
 
 struct C3Maps {
@@ -204,6 +206,7 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         const int N = p.layer[l].N, nst = p.layer[l].K / C3_KS;
         const uint32_t bytes = (uint32_t)N * 256u;              // two packed 16-wide chunks: hi | lo | hi | lo
         const float* wsrc = p.layer[l].wpack;
+        if (l == 0 && p.tile_group) wsrc += (int64_t)__ldg(p.tile_group + tile) * p.group_stride;
         for (int c = 0; c < nst; ++c, ++i) {
           const uint32_t s = i & ns_mask;
           C3_TRACE(40);
@@ -384,10 +387,10 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
           const float4 q = lds128(rowaddr + ((((uint32_t)j) ^ swz) << 4));
           x[4 * j] = q.x; x[4 * j + 1] = q.y; x[4 * j + 2] = q.z; x[4 * j + 3] = q.w;
         }
-        // the slot release must not overtake the loads (LDS and mbarrier.arrive run in different pipes): consume one
-        // register of each 16-byte load first
-        const float landed = ((x[0] + x[4]) + (x[8] + x[12])) + ((x[16] + x[20]) + (x[24] + x[28]));
-        asm volatile("" ::"f"(landed) : "memory");
+        // the slot release must not overtake the loads (LDS and mbarrier.arrive run in different pipes): really consume
+        // one register of each 16-byte load first (consume_loaded)
+        consume_loaded(((__float_as_uint(x[0]) ^ __float_as_uint(x[4])) ^ (__float_as_uint(x[8]) ^ __float_as_uint(x[12]))) ^
+                       ((__float_as_uint(x[16]) ^ __float_as_uint(x[20])) ^ (__float_as_uint(x[24]) ^ __float_as_uint(x[28]))));
         __syncwarp();
         if (lane == 0) mbar_arrive(raw_empty + 8 * sl);
         put_stage(i_base + (uint32_t)c, x);
@@ -684,6 +687,8 @@ int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, in
 
   p.V = V;
   p.trace = trace;
+  p.tile_group = layers[0].tile_group;
+  p.group_stride = layers[0].group_stride;
   p.nsrc = src.nsrc;
   int nmax = 0;
   for (int s = 0; s < src.nsrc; ++s) {

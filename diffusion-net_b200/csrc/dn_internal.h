@@ -34,7 +34,8 @@ struct DnLayer {
   int n_split;           //   (stacks [A_re; A_im] without a copy);  w_trans: input rows k >= n_split come from W2[k - n_split]
   const float* prepacked;  // optional: weights already in the tensor-core layout (tc_pack_layers)
   int pack_fmt;            // layout of `prepacked`: 0 = 16-wide chunks of [tf32 hi | tf32 lo] (round-1 kernels, 3xTF32);
-                           //   1 = 32-wide stages of [tf32 hi | bf16 (hi ; lo)] (rows_chain3_kernel, TF32 + bf16 corrections)
+                           //   1 = 32-wide stages of [tf32 hi | bf16 (hi ; lo)] (rows_chain3_kernel, TF32 + bf16 corrections);
+                           //   2 = 64-wide stages of bf16 (rows_chain16_kernel, DN_ENGINE_BF16)
   const float* bias;     // [N] or null
   int relu;
   const float* emul;     // optional elementwise multiplier [V][N] applied after the activation
@@ -46,6 +47,10 @@ struct DnLayer {
   float* out;            // optional [V][N] (ld_out); null => stays on chip (fused chain only)
   int64_t ld_out;
   int K, N;
+  // mesh batches (layer 0 of a chain only): `prepacked` holds one packed matrix per mesh, group_stride floats apart,
+  // and 128-row tile t uses matrix tile_group[t] (device array)
+  const int32_t* tile_group;
+  int64_t group_stride;
 };
 
 struct DnRowsSrc {
@@ -100,14 +105,24 @@ bool tc_supported_device();
 // Fused chain of up to DN_MAX_LAYERS layers over 128-row tiles; layer 0 reads `src`.
 int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers, int n_layers, int64_t V, int passes /*3 or 1*/,
                   void* ws, int64_t ws_bytes, cudaStream_t st);
-int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers);
+// `passes`: 3 = 3xTF32-grade (fp32 parity), 1 = single-pass TF32, DN_PASSES_BF16 = single-pass bf16 (DN_ENGINE_BF16)
+#define DN_PASSES_BF16 16
+int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers, int passes = 3);
 // packed-weight layout the kernel that will run this chain expects (sets layers[i].pack_fmt; call before tc_pack_layers)
-void tc_choose_pack_fmt(const DnRowsSrc& src, DnLayer* layers, int n_layers);
+void tc_choose_pack_fmt(const DnRowsSrc& src, DnLayer* layers, int n_layers, int passes = 3);
 // partial[p][k][c] for p < *P_out
+// `values` may be a column slice (row stride ld_values >= C) and a partial a slice of a wider one (row stride ldp):
+// C_width = 256 runs as two 128-column launches into the same [P][K][256] partials.  0 = contiguous (== C).
 int tc_to_basis_partial(const float* values, const float* basis, const float* massvec, int64_t V, int K, int C,
-                        float* partial, int* P_out, int passes, cudaStream_t st);
+                        float* partial, int* P_out, int passes, cudaStream_t st, int64_t ld_values = 0, int64_t ldp = 0,
+                        const int32_t* cta_rows = nullptr, int n_ctas = 0);
 int tc_to_basis_supported(int K, int C);
 int64_t tc_chain_ws_bytes(const DnLayer* layers, int n_layers);
+// mesh batches: pack S_b = exp(-evals_b t) * (partials of mesh b) for every mesh as layer0's per-mesh weights
+// (ws: n_meshes * tc_chain_ws_bytes(layer0, 1) bytes); sets layer0->prepacked / tile_group / group_stride
+int tc_pack_spectral_batched(DnLayer* layer0, int n_meshes, void* ws, int64_t ws_bytes, const float* partial,
+                             const int32_t* mesh_cta_begin, const float* evals, float* time, int clamp_writeback,
+                             const int32_t* tile_mesh, cudaStream_t st);
 // one launch: pack the weights of n layers into ws and set layers[i].prepacked
 int tc_pack_layers(DnLayer* layers, int n_layers, void* ws, int64_t ws_bytes, cudaStream_t st);
 // same, with layers[0] (w_trans, K = eigen count, N = channels) replaced by the spectral multiplier

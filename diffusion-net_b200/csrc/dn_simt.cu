@@ -435,7 +435,7 @@ __device__ __forceinline__ void fma2(unsigned long long& d, unsigned long long a
 }
 
 // ---------------------------------------------------------------------------------------------
-// Block gather (C = 128): one CTA per 64 consecutive rows.
+// Block gather (C a multiple of 128): one CTA per 64 consecutive rows.
 //   * the block's CSR metadata (rowptr slice, every (col, gx, gy) triple) is staged in shared memory by ONE coalesced
 //     pass: the per-row dependent chain rowptr -> colidx -> neighbour rows (three DRAM/L2 latencies in the warp-per-row
 //     kernel) becomes one latency per 64 rows plus the gathers themselves;
@@ -448,12 +448,12 @@ __device__ __forceinline__ void fma2(unsigned long long& d, unsigned long long a
 constexpr int GB_ROWS = 64;      // rows per CTA
 constexpr int GB_NNZ = 1024;     // staged entries per CTA (entries past it are read from global memory)
 
-template <bool ROT, int NB, int MINB>
+template <bool ROT, int NB, int MINB, int NH>
 __global__ void __launch_bounds__(256, MINB)
 spmm_features_blk_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                          const float2* __restrict__ vals, const float* __restrict__ xd,
                          const float* __restrict__ pq, int ld_pq, int64_t V, float* __restrict__ feat) {
-  constexpr int C = 128;
+  constexpr int C = 128 * NH;          // a warp covers 128 channels per pass (one float4 per lane), NH passes per row
   __shared__ int s_rp[GB_ROWS + 1];
   __shared__ int s_col[GB_NNZ];
   __shared__ float2 s_g[GB_NNZ];
@@ -472,10 +472,12 @@ spmm_features_blk_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
     }
   }
   __syncthreads();
-  const char* xb = reinterpret_cast<const char*>(xd) + lane * 16;
-  const char* pb = reinterpret_cast<const char*>(pq) + lane * 16;
+  constexpr int64_t x_row_bytes = (int64_t)C * 4;
   const int64_t pq_row_bytes = (int64_t)ld_pq * 4;
-  for (int r = warp; r < nrows; r += 8) {
+  for (int rh = warp; rh < nrows * NH; rh += 8) {
+    const int r = rh / NH, h = rh % NH;
+    const char* xb = reinterpret_cast<const char*>(xd) + h * 512 + lane * 16;
+    const char* pb = reinterpret_cast<const char*>(pq) + h * 512 + lane * 16;
     const int s = s_rp[r] - e0, e = s_rp[r + 1] - e0;
     unsigned long long gX0 = 0ull, gX1 = 0ull, gY0 = 0ull, gY1 = 0ull, re0 = 0ull, re1 = 0ull, im0 = 0ull, im1 = 0ull;
     for (int p0 = s; p0 < e; p0 += NB) {
@@ -490,10 +492,10 @@ spmm_features_blk_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
           if (p < GB_NNZ) { col = s_col[p]; g = s_g[p]; }
           else { col = __ldg(colidx + e0 + p); g = __ldg(vals + e0 + p); }
           wx[j] = g.x; wy[j] = g.y;
-          x[j] = __ldg(reinterpret_cast<const ulonglong2*>(xb + (int64_t)col * (C * 4)));
+          x[j] = __ldg(reinterpret_cast<const ulonglong2*>(xb + (int64_t)col * x_row_bytes));
           const char* pr = pb + (int64_t)col * pq_row_bytes;
           P[j] = __ldg(reinterpret_cast<const ulonglong2*>(pr));
-          if (ROT) Q[j] = __ldg(reinterpret_cast<const ulonglong2*>(pr + C * 4));
+          if (ROT) Q[j] = __ldg(reinterpret_cast<const ulonglong2*>(pr + x_row_bytes));
         }
       }
 #pragma unroll
@@ -522,7 +524,7 @@ spmm_features_blk_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
     o.y = feat_tanh(fmaf(gXv[1], rev[1], gYv[1] * imv[1]));
     o.z = feat_tanh(fmaf(gXv[2], rev[2], gYv[2] * imv[2]));
     o.w = feat_tanh(fmaf(gXv[3], rev[3], gYv[3] * imv[3]));
-    *reinterpret_cast<float4*>(feat + (base + r) * C + lane * 4) = o;
+    *reinterpret_cast<float4*>(feat + (base + r) * C + h * 128 + lane * 4) = o;
   }
 }
 
@@ -878,13 +880,14 @@ int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int 
     const char* e = getenv("DN_SPMM_BLK");
     use_blk = e ? atoi(e) : 1;   // measured (tools/ab_gather.py, V=200k): 1 -> 174 us (282 permuted) vs 181 (347) for the warp-per-row kernel
   }
-  if (C == 128 && use_blk) {
+  if ((C == 128 || C == 256) && use_blk) {
     const unsigned ctas = (unsigned)((V + GB_ROWS - 1) / GB_ROWS);
     const int ld = rotations ? 2 * C : C;
-    if (rotations)
-      spmm_features_blk_kernel<true, 7, 2><<<ctas, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, feat);
-    else
-      spmm_features_blk_kernel<false, 7, 2><<<ctas, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, feat);
+#define DN_BLK_LAUNCH(ROT_, NH_) \
+    spmm_features_blk_kernel<ROT_, 7, 2, NH_><<<ctas, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, feat)
+    if (rotations) { if (C == 128) DN_BLK_LAUNCH(true, 1); else DN_BLK_LAUNCH(true, 2); }
+    else { if (C == 128) DN_BLK_LAUNCH(false, 1); else DN_BLK_LAUNCH(false, 2); }
+#undef DN_BLK_LAUNCH
     DN_LAUNCH_CHECK();
     return DN_OK;
   }

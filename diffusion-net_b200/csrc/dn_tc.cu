@@ -81,6 +81,39 @@ struct PackJobs {
   int sp_P, sp_clamp;
 };
 
+// one weight element -> its place in the tensor-core layout `fmt` (DnLayer::pack_fmt)
+__device__ __forceinline__ void pack_store(float* dst, int fmt, int kc, int N, int k, int n, float w) {
+  if (fmt == 2) {
+    // bf16, 64-wide stages, K-major canonical (no swizzle): k-group (8 elements) stride N * 16 B, 8-row group stride
+    // 128 B, row stride 16 B  (rows_chain16_kernel)
+    const int st = k >> 6, kk = k & 63;
+    char* base = reinterpret_cast<char*>(dst) + (int64_t)st * N * 128;
+    *reinterpret_cast<__nv_bfloat16*>(base + (int64_t)(kk >> 3) * N * 16 + (int64_t)(n >> 3) * 128 + (n & 7) * 16 +
+                                      (kk & 7) * 2) = __float2bfloat16_rn(w);
+    return;
+  }
+  float hi, lo;
+  split_tf32(w, hi, lo);
+  if (fmt == 1) {
+    // 32-wide stage = [tf32 hi image: 8 k-groups of 4 | bf16 image: 4 k-groups of 8 of bf16(hi), then 4 of bf16(lo)],
+    // both K-major canonical (no swizzle): k-group stride N * 16 B, 8-row group stride 128 B, row stride 16 B
+    const int st = k >> 5, kk = k & 31;
+    char* base = reinterpret_cast<char*>(dst) + (int64_t)st * N * 256;
+    const int64_t rowoff = (int64_t)(n >> 3) * 128 + (n & 7) * 16;
+    *reinterpret_cast<float*>(base + (int64_t)(kk >> 2) * N * 16 + rowoff + (kk & 3) * 4) = hi;
+    char* b16 = base + (int64_t)N * 128;
+    *reinterpret_cast<__nv_bfloat16*>(b16 + (int64_t)(kk >> 3) * N * 16 + rowoff + (kk & 7) * 2) = __float2bfloat16_rn(hi);
+    *reinterpret_cast<__nv_bfloat16*>(b16 + (int64_t)(4 + (kk >> 3)) * N * 16 + rowoff + (kk & 7) * 2) =
+        __float2bfloat16_rn(w - hi);
+    return;
+  }
+  const int chunk = k / kc, kk = k % kc;
+  const int64_t img = (int64_t)N * kc;   // floats per image
+  const int64_t off = (int64_t)chunk * 2 * img + (int64_t)(kk >> 2) * (N * 4) + (n >> 3) * 32 + (n & 7) * 4 + (kk & 3);
+  dst[off] = hi;
+  dst[off + img] = lo;
+}
+
 // all weight matrices of a block forward in one launch (blocks are assigned to jobs by blk0)
 __global__ void pack_weights_kernel(const __grid_constant__ PackJobs jobs) {
   int ji = 0;
@@ -119,26 +152,37 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackJobs jobs) {
     else if (J.W2 && n >= J.n_split) w = J.W2[(int64_t)(n - J.n_split) * J.ldw + k];
     else w = J.W[(int64_t)n * J.ldw + k];
   }
-  float hi, lo;
-  split_tf32(w, hi, lo);
-  if (J.fmt == 1) {
-    // 32-wide stage = [tf32 hi image: 8 k-groups of 4 | bf16 image: 4 k-groups of 8 of bf16(hi), then 4 of bf16(lo)],
-    // both K-major canonical (no swizzle): k-group stride N * 16 B, 8-row group stride 128 B, row stride 16 B
-    const int st = k >> 5, kk = k & 31;
-    char* base = reinterpret_cast<char*>(J.dst) + (int64_t)st * N * 256;
-    const int64_t rowoff = (int64_t)(n >> 3) * 128 + (n & 7) * 16;
-    *reinterpret_cast<float*>(base + (int64_t)(kk >> 2) * N * 16 + rowoff + (kk & 3) * 4) = hi;
-    char* b16 = base + (int64_t)N * 128;
-    *reinterpret_cast<__nv_bfloat16*>(b16 + (int64_t)(kk >> 3) * N * 16 + rowoff + (kk & 7) * 2) = __float2bfloat16_rn(hi);
-    *reinterpret_cast<__nv_bfloat16*>(b16 + (int64_t)(4 + (kk >> 3)) * N * 16 + rowoff + (kk & 7) * 2) =
-        __float2bfloat16_rn(w - hi);
-    return;
+  pack_store(J.dst, J.fmt, kc, N, k, n, w);
+}
+
+// mesh batches: the spectral multiplier of every mesh, packed as layer-0 weights of the from_basis chain
+//   S_b[k][n] = exp(-evals[b][k] * max(t[n], 1e-8)) * sum_{p in CTAs of mesh b} partial[p][k][n]     (layers.py:48-49, 62-64)
+// grid (ceil(K*N/32), n_meshes), 256 threads: 32 consecutive elements x 8 slices of the partial sums per block
+__global__ void spectral_pack_batched_kernel(const float* __restrict__ partial, const int32_t* __restrict__ mesh_cta_begin,
+                                             const float* __restrict__ evals, float* time, int K, int N, int fmt, int kc,
+                                             float* dst, int64_t dst_stride_floats, int clamp) {
+  __shared__ float red[8][33];
+  const int b = blockIdx.y;
+  const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int idx = (int)blockIdx.x * 32 + e;
+  const int p0 = mesh_cta_begin[b], p1 = mesh_cta_begin[b + 1];
+  float acc = 0.f;
+  if (idx < K * N) {
+    const float* pp = partial + idx;
+    const int64_t stride = (int64_t)K * N;
+    for (int q = p0 + sl; q < p1; q += 8) acc += pp[(int64_t)q * stride];
   }
-  const int chunk = k / kc, kk = k % kc;
-  const int64_t img = (int64_t)N * kc;   // floats per image
-  const int64_t off = (int64_t)chunk * 2 * img + (int64_t)(kk >> 2) * (N * 4) + (n >> 3) * 32 + (n & 7) * 4 + (kk & 3);
-  J.dst[off] = hi;
-  J.dst[off + img] = lo;
+  red[sl][e] = acc;
+  __syncthreads();
+  if (sl != 0 || idx >= K * N) return;
+  const int k = idx / N, n = idx % N;
+  const float sum = ((red[0][e] + red[1][e]) + (red[2][e] + red[3][e])) + ((red[4][e] + red[5][e]) + (red[6][e] + red[7][e]));
+  const float t = fmaxf(time[n], 1e-8f);
+  const float w = expf(-(evals[(int64_t)b * K + k] * t)) * sum;
+  pack_store(dst + (int64_t)b * dst_stride_floats, fmt, kc, N, k, n, w);
+  // the in-place clamp of the reference: written back by mesh 0 only, after every reader of t[n] in this launch has at
+  // worst read either value (max(t, 1e-8) is idempotent)
+  if (clamp && b == 0 && k == K - 1) time[n] = t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -838,7 +882,10 @@ struct TcToBasisParams {
   int64_t V;
   int K, C, passes;
   int64_t chunks_per_cta;
-};
+  int64_t ld_values;     // row stride of `values` (floats): == C for a contiguous matrix, > C for a column slice
+  int64_t ldp;           // row stride of a partial (floats): partial[cta][k][ldp]
+  const int32_t* cta_rows;   // optional device [2 * grid]: the row range [begin, end) CTA i reduces (mesh batches: a CTA
+};                           //   never crosses a mesh boundary); null = uniform chunks_per_cta * 16 rows per CTA
 
 // TMEM columns: [0,128) correction terms (lo*hi + hi*lo); [128,256) [256,384) [384,512) three
 // round-robin accumulators for hi*hi.  Short, separate accumulation chains keep the truncation
@@ -869,24 +916,36 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int64_t total_chunks = (p.V + KC - 1) / KC;
-  const int64_t c_beg = (int64_t)blockIdx.x * p.chunks_per_cta;
-  int64_t c_end = c_beg + p.chunks_per_cta;
-  if (c_end > total_chunks) c_end = total_chunks;
-  const int64_t nch = c_end > c_beg ? c_end - c_beg : 0;
+  // this CTA reduces rows [rb, re) in chunks of KC (the last one may be short)
+  int64_t rb, re;
+  if (p.cta_rows) {
+    rb = p.cta_rows[2 * blockIdx.x];
+    re = p.cta_rows[2 * blockIdx.x + 1];
+  } else {
+    rb = (int64_t)blockIdx.x * p.chunks_per_cta * KC;
+    re = rb + p.chunks_per_cta * KC;
+    if (re > p.V) re = p.V;
+  }
+  const int64_t nch = re > rb ? (re - rb + KC - 1) / KC : 0;
 
   if (warp == 0) {
     // ===== TMA producer: 16 consecutive rows of Phi and of x are contiguous in HBM =====
     for (int64_t c = 0; c < nch; ++c) {
       const uint32_t s = c % TB_NST, ph = (c / TB_NST) & 1;
       mbar_wait(st_empty + 8 * s, ph ^ 1);
-      const int64_t v0 = (c_beg + c) * KC;
-      const int nv = (int)((p.V - v0) < KC ? (p.V - v0) : KC);
+      const int64_t v0 = rb + c * KC;
+      const int nv = (int)((re - v0) < KC ? (re - v0) : KC);
       const uint32_t ba = (uint32_t)nv * p.K * 4, bb = (uint32_t)nv * p.C * 4;
       if (elect_one()) {
         mbar_arrive_expect_tx(st_full + 8 * s, ba + bb);
         tma_bulk_g2s(smem_u32(raw + s * TB_RAW), p.basis + v0 * p.K, ba, st_full + 8 * s);
-        tma_bulk_g2s(smem_u32(raw + s * TB_RAW + TB_RAW_HALF), p.values + v0 * p.C, bb, st_full + 8 * s);
+        if (p.ld_values == p.C) {
+          tma_bulk_g2s(smem_u32(raw + s * TB_RAW + TB_RAW_HALF), p.values + v0 * p.C, bb, st_full + 8 * s);
+        } else {   // a column slice of a wider matrix: one copy per row
+          for (int j = 0; j < nv; ++j)
+            tma_bulk_g2s(smem_u32(raw + s * TB_RAW + TB_RAW_HALF) + (uint32_t)j * p.C * 4, p.values + (v0 + j) * p.ld_values,
+                         (uint32_t)p.C * 4, st_full + 8 * s);
+        }
       }
       __syncwarp();
     }
@@ -934,18 +993,18 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
     if (use_mass && nch > 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int64_t v = (c_beg + cset) * KC + 4 * vg + j;
-        mnext[j] = (v < p.V) ? __ldg(p.mass + v) : 0.f;
+        const int64_t v = rb + cset * KC + 4 * vg + j;
+        mnext[j] = (v < re) ? __ldg(p.mass + v) : 0.f;
       }
     }
     for (int64_t c = cset; c < nch; c += 2) {
-      const int64_t v0 = (c_beg + c) * KC + 4 * vg;
+      const int64_t v0 = rb + c * KC + 4 * vg;
       float m[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) m[j] = mnext[j];
       if (use_mass && c + 2 < nch) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mnext[j] = (v0 + 2 * KC + j < p.V) ? __ldg(p.mass + v0 + 2 * KC + j) : 0.f;
+        for (int j = 0; j < 4; ++j) mnext[j] = (v0 + 2 * KC + j < re) ? __ldg(p.mass + v0 + 2 * KC + j) : 0.f;
       }
       const uint32_t s = c % TB_NST, ph = (c / TB_NST) & 1;
       mbar_wait(st_full + 8 * s, ph);
@@ -954,7 +1013,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active && v0 + j < p.V)
+        if (active && v0 + j < re)
           q[j] = *reinterpret_cast<const float4*>(rp + (size_t)(4 * vg + j) * width * 4 + 16 * lane);
         q[j].x *= m[j]; q[j].y *= m[j]; q[j].z *= m[j]; q[j].w *= m[j];   // (values * massvec), geometry.py:583
       }
@@ -984,7 +1043,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
     }
     // ---- epilogue: sum the TMEM accumulators -> partial[cta][k][c]  (warps 2..5 = 4 lane quarters)
     if (cset == 0 && w < 4) {
-      float* out = p.partial + (int64_t)blockIdx.x * p.K * p.C;
+      float* out = p.partial + (int64_t)blockIdx.x * p.K * p.ldp;
       const int quarter = warp & 3;
       const int k = 32 * quarter + lane;
       if (nch > 0) {
@@ -1007,7 +1066,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) to_basis_kernel(const __grid_co
           }
         }
         if (k < p.K) {
-          float4* op = reinterpret_cast<float4*>(out + (int64_t)k * p.C + c0);
+          float4* op = reinterpret_cast<float4*>(out + (int64_t)k * p.ldp + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
@@ -1045,6 +1104,9 @@ static long long* take_trace_ptr() {
 int tc_chain3_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers);
 int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, int64_t V, int passes, int sm_count,
                    long long* trace, cudaStream_t st);
+// declared in dn_chain16.cu (bf16 engine)
+int tc_chain16_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers);
+int tc_rows_chain16(const DnRowsSrc& src, const DnLayer* layers, int n_layers, int64_t V, int sm_count, cudaStream_t st);
 
 static DevState* cur_dev_state() {
   int dev = 0;
@@ -1119,7 +1181,8 @@ static int tc_rows_chain_legacy_supported(const DnRowsSrc& src, const DnLayer* l
   return DN_OK;
 }
 
-int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers) {
+int tc_rows_chain_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layers, int passes) {
+  if (passes == DN_PASSES_BF16 && tc_chain16_supported(src, layers, n_layers) == DN_OK) return DN_OK;
   if (tc_chain3_supported(src, layers, n_layers) == DN_OK) return DN_OK;
   return tc_rows_chain_legacy_supported(src, layers, n_layers);
 }
@@ -1133,8 +1196,9 @@ static bool hybrid_enabled() {
   return on == 1;
 }
 
-void tc_choose_pack_fmt(const DnRowsSrc& src, DnLayer* layers, int n_layers) {
-  const int fmt = (hybrid_enabled() && tc_chain3_supported(src, layers, n_layers) == DN_OK) ? 1 : 0;
+void tc_choose_pack_fmt(const DnRowsSrc& src, DnLayer* layers, int n_layers, int passes) {
+  int fmt = (hybrid_enabled() && tc_chain3_supported(src, layers, n_layers) == DN_OK) ? 1 : 0;
+  if (passes == DN_PASSES_BF16 && tc_chain16_supported(src, layers, n_layers) == DN_OK) fmt = 2;
   for (int l = 0; l < n_layers; ++l) layers[l].pack_fmt = fmt;
 }
 
@@ -1175,6 +1239,24 @@ int tc_pack_layers_spectral(DnLayer* layers, int n_layers, void* ws, int64_t ws_
   return DN_OK;
 }
 
+int tc_pack_spectral_batched(DnLayer* layer0, int n_meshes, void* ws, int64_t ws_bytes, const float* partial,
+                             const int32_t* mesh_cta_begin, const float* evals, float* time, int clamp_writeback,
+                             const int32_t* tile_mesh, cudaStream_t st) {
+  if (!layer0 || n_meshes < 1 || !ws || !partial || !mesh_cta_begin || !evals || !time || !tile_mesh)
+    return DN_ERR_INVALID_ARGUMENT;
+  const int64_t per = tc_chain_ws_bytes(layer0, 1);
+  if (per * n_meshes > ws_bytes) return DN_ERR_WORKSPACE;
+  const int K = layer0->K, N = layer0->N;
+  dim3 grid((unsigned)((K * N + 31) / 32), (unsigned)n_meshes);
+  spectral_pack_batched_kernel<<<grid, 256, 0, st>>>(partial, mesh_cta_begin, evals, time, K, N, layer0->pack_fmt, KC,
+                                                     static_cast<float*>(ws), per / 4, clamp_writeback);
+  DN_LAUNCH_CHECK();
+  layer0->prepacked = static_cast<float*>(ws);
+  layer0->tile_group = tile_mesh;
+  layer0->group_stride = per / 4;
+  return DN_OK;
+}
+
 int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers_in, int n_layers, int64_t V, int passes, void* ws,
                   int64_t ws_bytes, cudaStream_t st) {
   if (V <= 0) return DN_OK;
@@ -1187,15 +1269,21 @@ int tc_rows_chain(const DnRowsSrc& src, const DnLayer* layers_in, int n_layers, 
     packed = packed && layers[l].prepacked != nullptr;
   }
   if (!packed) {
-    tc_choose_pack_fmt(src, layers, n_layers);
+    tc_choose_pack_fmt(src, layers, n_layers, passes);
     int rc = tc_pack_layers(layers, n_layers, ws, ws_bytes, st);
     if (rc) return rc;
+  }
+  if (passes == DN_PASSES_BF16) {
+    // bf16 engine: the SS bf16 chain when the shapes fit it (weights packed as bf16), single-pass TF32 otherwise
+    if (layers[0].pack_fmt == 2) return tc_rows_chain16(src, layers, n_layers, V, dv->sms, st);
+    passes = 1;
   }
   // default: the TMA-fed kernel of dn_chain.cu; shapes outside its envelope run the round-1 kernels below
   if (tc_chain3_supported(src, layers, n_layers) == DN_OK) {
     const int rc = tc_rows_chain3(src, layers, n_layers, V, passes, dv->sms, take_trace_ptr(), st);
     if (rc != DN_ERR_UNSUPPORTED) return rc;
   }
+  if (layers[0].tile_group) return DN_ERR_UNSUPPORTED;              // per-mesh layer-0 weights: chain3 / chain16 only
   for (int l = 0; l < n_layers; ++l)
     if (layers[l].pack_fmt != 0) return DN_ERR_INVALID_ARGUMENT;     // the round-1 kernels read the 16-wide chunk layout
   if (tc_rows_chain_legacy_supported(src, layers, n_layers) != DN_OK) return DN_ERR_UNSUPPORTED;
@@ -1254,14 +1342,27 @@ int tc_to_basis_supported(int K, int C) {
 }
 
 int tc_to_basis_partial(const float* values, const float* basis, const float* massvec, int64_t V, int K, int C,
-                        float* partial, int* P_out, int passes, cudaStream_t st) {
+                        float* partial, int* P_out, int passes, cudaStream_t st, int64_t ld_values, int64_t ldp,
+                        const int32_t* cta_rows, int n_ctas) {
   DevState* dv = cur_dev_state();
   if (!dv || dv->ok != 1) return DN_ERR_NOT_SM100;
-  if ((reinterpret_cast<uintptr_t>(values) & 15) || (reinterpret_cast<uintptr_t>(basis) & 15))
+  if (ld_values <= 0) ld_values = C;
+  if (ldp <= 0) ldp = C;
+  if ((reinterpret_cast<uintptr_t>(values) & 15) || (reinterpret_cast<uintptr_t>(basis) & 15) || (ld_values % 4) ||
+      (ldp % 4) || (reinterpret_cast<uintptr_t>(partial) & 15))
     return DN_ERR_UNSUPPORTED;
   TcToBasisParams p;
   p.values = values; p.basis = basis; p.mass = massvec; p.partial = partial;
-  p.V = V; p.K = K; p.C = C; p.passes = passes;
+  p.ld_values = ld_values; p.ldp = ldp; p.cta_rows = cta_rows;
+  if (cta_rows) {                       // batch of meshes: the caller planned the CTAs (dn_mesh_batch_plan)
+    if (n_ctas < 1) return DN_ERR_INVALID_ARGUMENT;
+    p.V = V; p.K = K; p.C = C; p.passes = (passes == 3) ? 3 : 1; p.chunks_per_cta = 0;
+    to_basis_kernel<<<n_ctas, TB_THREADS, TB_SMEM, st>>>(p);
+    DN_LAUNCH_CHECK();
+    *P_out = n_ctas;
+    return DN_OK;
+  }
+  p.V = V; p.K = K; p.C = C; p.passes = (passes == 3) ? 3 : 1;
   const int64_t total_chunks = (V + KC - 1) / KC;
   int grid = dv->sms;
   if (total_chunks < grid) grid = (int)(total_chunks > 0 ? total_chunks : 1);

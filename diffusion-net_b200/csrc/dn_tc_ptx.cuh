@@ -199,6 +199,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+// A REAL consumer of loaded registers: xor them and branch on the result (never taken in practice).  In-order issue then
+// guarantees every instruction after this one issues after the loads that produced `v...` have returned their data.
+// Needed before releasing a shared-memory slot that was read with ld.shared: mbarrier.arrive runs in a different pipe
+// and can overtake loads whose results nobody has consumed yet, and an empty asm("" :: "f"(x)) "use" leaves no
+// instruction behind for ptxas to keep (measured: rows_chain16_kernel lost whole stages that way).
+__device__ __forceinline__ void consume_loaded(uint32_t d) {
+  asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %0, 0x7fedbeef;\n@p trap;\n}" ::"r"(d) : "memory");
+}
+
 // error-compensated split  x ~= hi + lo  with hi, lo exactly representable in TF32
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   uint32_t h, l;

@@ -229,6 +229,46 @@ class DiffusionNet(nn.Module):
         B = x.shape[0]
         return torch.stack([ops.mlp_apply([x[b]], [lin.weight], [lin.bias]) for b in range(B)], 0)
 
+    def forward_batch(self, batch, xs):
+        """Inference over a ``batch.MeshBatch`` of independent meshes in ONE launch sequence (BASELINE config 4): the
+        reference's per-mesh loop (layers.py:217-222, 366-401) with every stage of every block launched once over all
+        meshes (``dn_block_fwd_batched``).  ``xs``: list of per-mesh (V_b, C_in) features, or one tensor already in the
+        batch layout.  Returns the list of per-mesh outputs (views into one tensor); 'vertices' and 'global_mean'
+        outputs only.  Equal to ``[self(x_b, mass_b, ...) for b]`` (tests/test_gpu_parity.py)."""
+        from . import batch as _batch
+        if self.outputs_at not in ('vertices', 'global_mean'):
+            raise ValueError("forward_batch supports outputs_at 'vertices' and 'global_mean'")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("forward_batch is an inference path: call it under torch.no_grad()")
+        if self.diffusion_method != 'spectral':
+            raise NotImplementedError("forward_batch: spectral diffusion only")
+        x = xs if torch.is_tensor(xs) else batch.pack(xs)
+        if x.shape[-1] != self.C_in:
+            raise ValueError("DiffusionNet was constructed with C_in={}, but x_in has last dim={}".format(
+                self.C_in, x.shape[-1]))
+        x = ops.mlp_apply([x], [self.first_lin.weight], [self.first_lin.bias])
+        for blk in self.blocks:
+            if blk.training and blk.dropout:
+                raise RuntimeError("forward_batch: eval mode only (dropout)")
+            A_re = A_im = None
+            if blk.with_gradient_features:
+                A_re, A_im = blk.gradient_features.weights()
+            lins = blk.mlp.linears()
+            x = _batch.block_forward_batched_raw(batch, x, blk.diffusion.diffusion_time, A_re, A_im,
+                                                 [l.weight for l in lins], [l.bias for l in lins],
+                                                 blk.with_gradient_features)
+        x = ops.mlp_apply([x], [self.last_lin.weight], [self.last_lin.bias])
+        outs = batch.unpack(x)
+        if self.outputs_at == 'global_mean':
+            res = []
+            for b, o in enumerate(outs):
+                m = batch.mass[batch.row_begin[b]:batch.row_begin[b] + batch.n_rows[b]]
+                res.append((o * (m / m.sum()).unsqueeze(-1)).sum(dim=-2))
+            outs = res
+        if self.last_activation != None:
+            outs = [self.last_activation(o) for o in outs]
+        return outs
+
     def forward(self, x_in, mass, L=None, evals=None, evecs=None, gradX=None, gradY=None, edges=None, faces=None):
         """[N,C] or [B,N,C] in, [N,C_out] or [B,N,C_out] out (reference layers.py:314-407)."""
         if x_in.shape[-1] != self.C_in:

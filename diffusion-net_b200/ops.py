@@ -14,14 +14,14 @@ import torch
 
 from . import _lib
 
-_ENGINES = {"simt": _lib.ENGINE_SIMT, "tc3x": _lib.ENGINE_TC3X, "tc1x": _lib.ENGINE_TC1X}
+_ENGINES = {"simt": _lib.ENGINE_SIMT, "tc3x": _lib.ENGINE_TC3X, "tc1x": _lib.ENGINE_TC1X, "bf16": _lib.ENGINE_BF16}
 _engine = _ENGINES[os.environ.get("DN_B200_ENGINE", "tc3x")]
 
 
 def set_engine(name: str):
     """'tc3x' (default: tcgen05, error-compensated 3xTF32, fp32-grade), 'tc1x' (single-pass
-    TF32) or 'simt' (exact fp32 FFMA).  Shapes outside the tcgen05 kernels' envelope always
-    run the exact SIMT kernels."""
+    TF32), 'bf16' (single-pass bf16 tensor-core arithmetic, fp32 tensors in HBM; ~1e-2) or 'simt'
+    (exact fp32 FFMA).  Shapes outside the tcgen05 kernels' envelope always run the exact SIMT kernels."""
     global _engine
     _engine = _ENGINES[name]
 
@@ -58,10 +58,11 @@ _retired_workspaces = []
 pin_workspaces = False      # set by graphs.GraphedNet: never free a workspace a graph may point into
 
 
-def workspace(V, K, C_, device):
+def workspace(V, K, C_, device, extra=0):
     """Scratch for the C-ABI calls, one buffer per (device, stream): calls on different streams
-    (graphs.GraphedNet replays meshes concurrently) never share scratch."""
-    need = _lib.load().dn_workspace_bytes(int(V), int(K), int(C_))
+    (graphs.GraphedNet replays meshes concurrently) never share scratch.  ``extra``: bytes on top of
+    dn_workspace_bytes (mesh batches: one packed spectral multiplier per mesh)."""
+    need = _lib.load().dn_workspace_bytes(int(V), int(K), int(C_)) + int(extra) + 4096
     dev_index = device.index if device.index is not None else torch.cuda.current_device()
     key = (dev_index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)

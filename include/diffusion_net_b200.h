@@ -21,6 +21,8 @@
  *   DN_ENGINE_TC3X  tcgen05 tensor cores, error-compensated 3xTF32 (fp32-grade,
  *                   the default product path; <=1e-5 relative vs the reference)
  *   DN_ENGINE_TC1X  tcgen05 single-pass TF32 (fast, ~5e-4 relative)
+ *   DN_ENGINE_BF16  tcgen05 single-pass bf16 (kind::f16, fp32 accumulate; ~1e-2 relative; layers up to
+ *                   256 wide chain on chip: BASELINE config 3, C_width = 256).  Tensors stay fp32 in HBM.
  */
 #ifndef DIFFUSION_NET_B200_H
 #define DIFFUSION_NET_B200_H
@@ -32,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 3
+#define DN_ABI_VERSION 4
 
 typedef void* dn_stream_t; /* cudaStream_t */
 
@@ -44,7 +46,7 @@ enum dn_status {
   DN_ERR_NOT_SM100 = -4         /* tensor-core engine requested on a non-sm_100 GPU */
 };
 
-enum dn_engine { DN_ENGINE_SIMT = 0, DN_ENGINE_TC3X = 1, DN_ENGINE_TC1X = 2 };
+enum dn_engine { DN_ENGINE_SIMT = 0, DN_ENGINE_TC3X = 1, DN_ENGINE_TC1X = 2, DN_ENGINE_BF16 = 3 };
 
 /* Shared-pattern CSR form of the (gradX, gradY) pair.  The reference hands over two
  * coalesced COO tensors with identical, row-sorted sparsity (Re/Im of one complex
@@ -221,6 +223,36 @@ int dn_block_fwd_profile(const float* x_in, const float* mass, const float* eval
                          const dn_csr* grad, const dn_block_params* params, int64_t V, int K, int C,
                          float* out, void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream,
                          float* stage_ms_host);
+
+/* ---- batches of independent meshes in one launch sequence (BASELINE config 4) -------------------
+ * The reference loops over the batch dimension with one set of operators per mesh (layers.py:217-222; a DataLoader
+ * of batch_size None in every experiment).  Here a batch is ONE vertex range: mesh b occupies rows
+ * [row_begin[b], row_begin[b] + n_rows[b]) of every (V, .) array; row_begin[b] is a multiple of 128 (a 128-row tile
+ * never straddles two meshes); rows in the padding between meshes carry mass 0, basis 0 and no CSR entries; the CSR
+ * is block diagonal with batch-global column indices; evals is (n_meshes, K).  Every per-vertex stage (gather,
+ * MiniMLP) then runs as one launch over the whole range, and the per-mesh spectral stages run grouped:
+ * to_basis CTAs never cross a mesh (tb_rows), the spectral multiplier is packed once per mesh and the from_basis chain
+ * picks its weights per tile (tile_mesh).  Device arrays are built once per batch from dn_mesh_batch_plan's output. */
+typedef struct dn_mesh_batch {
+  int32_t n_meshes;
+  int32_t n_tb_ctas;             /* CTAs of the grouped to_basis launch (<= 1024)                             */
+  const int32_t* tile_mesh;      /* device [V / 128]: mesh of every 128-row tile                              */
+  const int32_t* tb_rows;        /* device [2 * n_tb_ctas]: row range [begin, end) of each to_basis CTA       */
+  const int32_t* mesh_cta_begin; /* device [n_meshes + 1]: the CTAs of mesh b are [begin[b], begin[b+1])      */
+} dn_mesh_batch;
+
+/* HOST-side planner (all pointers are HOST pointers): lays n_meshes meshes of n_rows_host[b] vertices out in one
+ * row range (each start rounded up to 128) and splits them over about sm_count to_basis CTAs.
+ * Outputs (caller-allocated): row_begin_host [n_meshes + 1] (last = padded total V), tile_mesh_host [V / 128],
+ * tb_rows_host [2 * 1024], mesh_cta_begin_host [n_meshes + 1].  Returns the number of to_basis CTAs or DN_ERR_*. */
+int dn_mesh_batch_plan(int n_meshes, const int32_t* n_rows_host, int sm_count, int32_t* row_begin_host,
+                       int32_t* tile_mesh_host, int32_t* tb_rows_host, int32_t* mesh_cta_begin_host);
+
+/* dn_block_fwd over a batch laid out as above (V = padded total, a multiple of 128).  Tensor-core engines only
+ * (DN_ERR_UNSUPPORTED otherwise and for shapes outside the fused kernels' envelope: the caller loops over meshes). */
+int dn_block_fwd_batched(const float* x_in, const float* mass, const float* evals, const float* evecs,
+                         const dn_csr* grad, const dn_block_params* params, const dn_mesh_batch* batch, int64_t V,
+                         int K, int C, float* out, void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream);
 
 #ifdef __cplusplus
 }

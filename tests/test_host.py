@@ -24,7 +24,7 @@ def test_library_builds_and_exports_header_symbols():
     assert declared == set(dn._lib.SIGNATURES), declared ^ set(dn._lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dn_abi_version() == 3
+    assert lib.dn_abi_version() == 4
     assert lib.dn_error_string(-3).decode().startswith("diffusion_net_b200: workspace")
     assert lib.dn_workspace_bytes(200000, 128, 128) > 0
     assert lib.dn_workspace_bytes(-1, 128, 128) == -1
@@ -229,3 +229,35 @@ def test_patch_build_covers_every_row_once_and_reproduces_the_spmm(permute):
                 out[tgt[i]] = np.dot(vals_p[e0:e1], x[src[lcol[e0:e1]]])
         assert np.allclose(out, A @ x, rtol=1e-12, atol=1e-12)
     assert _patch_build(rp, ci, V, 64, 3)[0] == -2                              # a row longer than max_src
+
+
+def test_mesh_batch_plan_host():
+    """dn_mesh_batch_plan (host-only): 128-aligned mesh starts, tile -> mesh table, to_basis CTAs that tile every
+    mesh exactly and never cross one."""
+    import ctypes as C
+    import numpy as np
+    import diffusion_net_b200 as dn
+    lib = dn._lib.load()
+    for n_rows in ([1800, 2200, 1, 0, 129, 128, 4000], [2000] * 32, [200000], [5] * 300):
+        B = len(n_rows)
+        nr = np.asarray(n_rows, dtype=np.int32)
+        row_begin = np.zeros(B + 1, dtype=np.int32)
+        tile_mesh = np.full(sum((v + 127) // 128 for v in n_rows) + 1, -1, dtype=np.int32)
+        tb_rows = np.zeros(2048, dtype=np.int32)
+        cta_begin = np.zeros(B + 1, dtype=np.int32)
+        n = lib.dn_mesh_batch_plan(B, nr.ctypes.data, 148, row_begin.ctypes.data, tile_mesh.ctypes.data,
+                                   tb_rows.ctypes.data, cta_begin.ctypes.data)
+        assert 1 <= n <= 1024
+        assert cta_begin[0] == 0 and cta_begin[B] == n
+        for b in range(B):
+            assert row_begin[b] % 128 == 0 and row_begin[b + 1] - row_begin[b] == (n_rows[b] + 127) // 128 * 128
+            assert (tile_mesh[row_begin[b] // 128:row_begin[b + 1] // 128] == b).all()
+            lo, hi = cta_begin[b], cta_begin[b + 1]
+            assert hi > lo
+            cur = row_begin[b]
+            for c in range(lo, hi):
+                rb, re = tb_rows[2 * c], tb_rows[2 * c + 1]
+                assert rb == cur and (re > rb or n_rows[b] == 0) and (rb - row_begin[b]) % 16 == 0
+                cur = re
+            assert cur == row_begin[b] + n_rows[b]
+    assert lib.dn_mesh_batch_plan(0, None, 148, None, None, None, None) < 0

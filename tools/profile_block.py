@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import diffusion_net_b200 as dn
 
-n, m, K, C = 400, 500, 128, 128
+n, m, K, C = 400, 500, 128, int(os.environ.get("DN_PROFILE_C", "128"))
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 dn.set_engine(os.environ.get("DN_B200_ENGINE", "tc3x"))
 mass, L, evals, evecs, gX, gY = dn.synthetic.structural_operators(n, m, K, seed=0, device="cuda")
