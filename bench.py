@@ -484,6 +484,9 @@ def run_aux(args, rank, world, local):
         x_cat = mb.pack([it["x_in"] for it in items])
         with torch.no_grad():
             ms, launches = timed(lambda: net.forward_batch(mb, x_cat))
+            # (a') the same launch sequence replayed as ONE CUDA graph
+            gb = dn.graphs.GraphedBatch(net, mb)
+            ms_graph1, _ = timed(lambda: gb.forward(x_cat))
             # (b) round 1's route for comparison: per-mesh launches replayed from CUDA graphs on 4 streams
             gn = dn.graphs.GraphedNet(net, n_streams=4)
             ms_graphs, _ = timed(lambda: gn.forward_batch(items))
@@ -496,7 +499,7 @@ def run_aux(args, rank, world, local):
                      "config": {"workload": "small_batch 32 meshes V~2k K=128 C=128 4 blocks, sharded x{}".format(world),
                                 "engine": args.engine, "meshes_per_rank": len(mine),
                                 "route": "MeshBatch: one batched launch per stage (dn_block_fwd_batched)",
-                                "padded_rows": mb.V, "per_mesh_cuda_graphs_ms": ms_graphs,
+                                "padded_rows": mb.V, "one_cuda_graph_ms": ms_graph1, "per_mesh_cuda_graphs_ms": ms_graphs,
                                 "max_rel_diff_vs_per_mesh": err},
                      "gpu_launches": launches})
     if rank == 0:

@@ -1,6 +1,8 @@
 // C-ABI entry points (include/diffusion_net_b200.h).  Argument checking, workspace carving and
 // the kernel sequence of each reference function; no torch types, no hidden synchronisation.
 #include "dn_internal.h"
+#include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 #include <string.h>
 
@@ -25,6 +27,29 @@ constexpr int64_t kPartialFloats = 16ll << 20;  // 64 MiB split-V partial sums
 inline bool use_tc(int engine) { return engine == DN_ENGINE_TC3X || engine == DN_ENGINE_TC1X || engine == DN_ENGINE_BF16; }
 inline int tc_passes(int engine) { return engine == DN_ENGINE_TC1X ? 1 : (engine == DN_ENGINE_BF16 ? DN_PASSES_BF16 : 3); }
 
+// A tensor-core engine was requested but this contraction is outside the tcgen05 kernels' envelope and runs the exact
+// fp32 SIMT kernel instead (same result class or better, slower).  Said once per shape on stderr; DN_STRICT_TC=1 turns
+// it into DN_ERR_UNSUPPORTED so that a deployment never runs the slow path unnoticed.  A non-sm_100 device with a
+// tensor-core engine is always an error (DN_ERR_NOT_SM100): there is no multi-backend dispatch.
+int note_simt_fallback(const char* what, int K, int N) {
+  static int strict = -1;
+  if (strict < 0) { const char* e = getenv("DN_STRICT_TC"); strict = (e && atoi(e)) ? 1 : 0; }
+  static int seen[64][2];
+  static int nseen = 0;
+  bool first = true;
+  for (int i = 0; i < nseen; ++i) if (seen[i][0] == K && seen[i][1] == N) first = false;
+  if (first && nseen < 64) {
+    seen[nseen][0] = K; seen[nseen][1] = N; ++nseen;
+    fprintf(stderr, "diffusion_net_b200: %s with K=%d, N=%d is outside the tensor-core kernels' envelope; running the exact "
+                    "fp32 SIMT kernel%s\n", what, K, N, strict ? " is refused (DN_STRICT_TC=1)" : "");
+  }
+  return strict ? DN_ERR_UNSUPPORTED : DN_OK;
+}
+#define DN_TC_DEVICE_OR_FAIL(engine)                                              \
+  do {                                                                            \
+    if (use_tc(engine) && !tc_supported_device()) return DN_ERR_NOT_SM100;        \
+  } while (0)
+
 inline DnLayer make_layer(const float* W, int64_t ldw, int w_trans, const float* bias, int relu, int K, int N,
                           float* out, int64_t ld_out) {
   DnLayer L;
@@ -45,6 +70,7 @@ inline DnRowsSrc one_src(const float* p, int width, int64_t ld) {
 // `tmp0/tmp1` are V x maxN ping-pong buffers used only by the unfused SIMT route.
 int run_chain(const DnRowsSrc& src, DnLayer* layers, int n_layers, int64_t V, int engine, float* tmp0,
               float* tmp1, void* tc_ws, int64_t tc_ws_bytes, cudaStream_t st) {
+  DN_TC_DEVICE_OR_FAIL(engine);
   const bool tc = use_tc(engine) && tc_supported_device();
   if (tc && tc_rows_chain_supported(src, layers, n_layers, tc_passes(engine)) == DN_OK) {
     return tc_rows_chain(src, layers, n_layers, V, tc_passes(engine), tc_ws, tc_ws_bytes, st);
@@ -65,8 +91,10 @@ int run_chain(const DnRowsSrc& src, DnLayer* layers, int n_layers, int64_t V, in
     int rc;
     if (tc && tc_rows_chain_supported(cur, &L, 1, tc_passes(engine)) == DN_OK)
       rc = tc_rows_chain(cur, &L, 1, V, tc_passes(engine), tc_ws, tc_ws_bytes, st);
-    else
+    else {
+      if (use_tc(engine) && (rc = note_simt_fallback("a dense layer", L.K, L.N))) return rc;
       rc = simt_rows_gemm(cur, L, V, st);
+    }
     if (rc) return rc;
     cur = one_src(o, L.N, ldo);
   }
@@ -88,6 +116,8 @@ int to_basis_partials(const float* values, const float* basis, const float* mass
     }
     return DN_OK;
   }
+  DN_TC_DEVICE_OR_FAIL(engine);
+  if (use_tc(engine)) { const int rc = note_simt_fallback("to_basis", K, C); if (rc) return rc; }
   // out[k][c] = sum_v basis[v][k] * (mass[v] * values[v][c])
   return simt_atb_partial_st(basis, K, K, values, C, C, massvec, V, partial, partial_floats, P, st);
 }
@@ -104,6 +134,8 @@ int atb(const float* A, int64_t lda, int I, const float* B, int64_t ldb, int J, 
     if (rc == DN_OK) return launch_reduce_partials_ld(part, P, I, J, out, ld_out, accumulate, st);
     if (rc != DN_ERR_UNSUPPORTED) return rc;
   }
+  DN_TC_DEVICE_OR_FAIL(engine);
+  if (use_tc(engine)) { const int rc = note_simt_fallback("a weight gradient", I, J); if (rc) return rc; }
   return simt_atb(A, lda, I, B, ldb, J, nullptr, V, out, ld_out, accumulate, part, part_floats, st);
 }
 
@@ -111,6 +143,8 @@ int atb(const float* A, int64_t lda, int I, const float* B, int64_t ldb, int J, 
 int one_layer(const DnRowsSrc& src, DnLayer& L, int64_t V, int engine, void* tc_ws, int64_t tc_ws_bytes, cudaStream_t st) {
   if (use_tc(engine) && tc_supported_device() && tc_rows_chain_supported(src, &L, 1, tc_passes(engine)) == DN_OK)
     return tc_rows_chain(src, &L, 1, V, tc_passes(engine), tc_ws, tc_ws_bytes, st);
+  DN_TC_DEVICE_OR_FAIL(engine);
+  if (use_tc(engine)) { const int rc = note_simt_fallback("a dense layer", L.K, L.N); if (rc) return rc; }
   return simt_rows_gemm(src, L, V, st);
 }
 

@@ -59,3 +59,38 @@ class GraphedNet:
         for st in used:
             cur.wait_stream(st)
         return outs
+
+
+class GraphedBatch:
+    """One CUDA graph for ``net.forward_batch(batch, x)`` over a ``batch.MeshBatch``: the ~27 launches of a 4-block
+    net over ALL meshes of the batch replay as one graph launch (BASELINE config 4).  ``forward(x)`` copies ``x``
+    (batch layout, or a per-mesh list) into the graph's static input and replays; the returned per-mesh outputs are
+    views of the static output buffer (overwritten by the next call).  Inference only."""
+
+    def __init__(self, net, batch):
+        self.net, self.batch = net, batch
+        self.device = batch.device
+        ops.pin_workspaces = True
+        self.x = torch.zeros(batch.V, net.C_in, dtype=torch.float32, device=self.device)
+        self.graph = None
+        self.outs = None
+
+    def _capture(self):
+        st = torch.cuda.Stream(device=self.device)
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(st), torch.no_grad():
+            for _ in range(2):
+                self.net.forward_batch(self.batch, self.x)
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(g, stream=st):
+            outs = self.net.forward_batch(self.batch, self.x)
+        self.graph, self.outs, self._stream = g, outs, st
+
+    def forward(self, xs):
+        x = xs if torch.is_tensor(xs) else self.batch.pack(xs)
+        self.x.copy_(x)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        return self.outs

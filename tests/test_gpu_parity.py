@@ -422,6 +422,12 @@ def test_forward_batch_equals_per_mesh(dn, engine, C):
         with torch.no_grad():
             outs = net.forward_batch(mb, xs)
             outs2 = net.forward_batch(mb, mb.pack(xs))
+            if engine == "tc3x" and C == 128:                  # one CUDA graph for the whole batched forward
+                gb = dn.graphs.GraphedBatch(net, mb)
+                for _ in range(2):
+                    og = gb.forward(xs)
+                    torch.cuda.synchronize()
+                    assert all(torch.equal(a, b) for a, b in zip(og, outs))
         tol = 2e-5 if engine == "tc3x" else BF16_TOL
         for o, o2, r in zip(outs, outs2, refs):
             assert o.shape == r.shape
