@@ -727,10 +727,12 @@ def main():
             "spectral_scale": (0, 0, "(separate launch only on the SIMT engine; part of pack_weights_kernel here)"),
             "pack_weights": (4 * 148 * K * C + 3 * 4 * (K * C + 2 * C * C + 5 * C * C), 0,
                              "pack_weights_kernel (split-V partial reduction + exp(-lambda t) scale + hi/lo weight pack)"),
-            "from_basis_pq": (4 * V * (K + C + 2 * C), (2 * K * C + 4 * C * C) * V,
-                              "rows_chain3_kernel (from_basis -> [P|Q], 2 fused layers)"),
-            "grad_features_gather": (4 * V * (3 * C + C) + 12 * nnz + 4 * V, 12 * NNZ_ROW * C * V,
-                                     "spmm_features_kernel (CSR gather + inner product + tanh)"),
+            # default route at C = 128 (DN_GF_TC=1): from_basis alone, then the gradient features as an x-only gather
+            # (writes [gX|gY]) + two tcgen05 GEMM launches with the inner product / tanh epilogue
+            "from_basis_pq": (4 * V * (K + C), 2 * K * C * V, "rows_chain3_kernel (from_basis)"),
+            "grad_features_gather": (4 * V * (C + 2 * C) + 12 * nnz + 4 * V + 4 * V * (2 * C + C), (4 * NNZ_ROW * C + 8 * C * C) * V,
+                                     "spmm_gxy_blk_kernel (x-only CSR gather) + 2 x rows_chain3_kernel ([gX|gY] W_rot, "
+                                     "tanh(gX*Bre+gY*Bim) epilogue)"),
             "mlp": (4 * V * (3 * C + C), 10 * C * C * V, "rows_chain3_kernel (MiniMLP + skip, 3 fused layers)"),
         }
         try:   # per-launch DRAM traffic of each kernel from the committed ncu --set full capture of this command

@@ -151,6 +151,11 @@ int one_layer(const DnRowsSrc& src, DnLayer& L, int64_t V, int engine, void* tc_
 }  // namespace
 
 long long g_dn_launches = 0;
+// bring-up: device time of the x-only gather inside stage [4] of the last dn_block_fwd_profile call (tools only)
+static cudaEvent_t g_gf_ev = nullptr;
+static float g_gf_gather_ms = 0.f;
+static bool g_gf_recorded = false;
+extern "C" float dn_debug_gf_gather_ms(void) { return g_gf_gather_ms; }
 
 extern "C" {
 
@@ -634,7 +639,27 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
   DnLayer L[3 + DN_MAX_LAYERS];
   L[0] = make_layer(S, C, 1, nullptr, 0, K, C, xd, C);
   int nfront = 1;
-  if (p->with_gradient_features) {
+  // Tensor-core gradient features (C_width = 128, learned rotations, fp32-grade / TF32 engines): gather only x_diffuse
+  // (gxy = [gradX x | gradY x], a third of the commuted route's gather traffic), then the complex-linear map as tcgen05
+  // GEMMs whose epilogue forms tanh(gX * Bre + gY * Bim) (layers.py:117-130) -- two launches of 64 channels each, so
+  // that the [Bre | Bim] accumulators (128 columns) ping-pong in TMEM.  DN_GF_TC=0 restores the commuted route
+  // ([P|Q] = x_diffuse [A_re; A_im]^T in front of a gather of x, P and Q).
+  static int gf_env = -1;
+  if (gf_env < 0) { const char* e = getenv("DN_GF_TC"); gf_env = (!e || atoi(e) != 0) ? 1 : 0; }
+  bool gf_tc = false;
+  DnRowsSrc src_gxy = one_src(pq, 2 * C, 2 * C);
+  if (p->with_gradient_features && rot && C == 128 && gf_env && use_tc(engine) && engine != DN_ENGINE_BF16 &&
+      tc_supported_device() && !(grad->patches && grad->patches->n_patches > 0)) {
+    for (int h = 0; h < 2; ++h) {
+      L[1 + h] = make_layer(p->A_re, C, 0, nullptr, 0, 2 * C, C, feat + h * 64, C);
+      L[1 + h].W2 = p->A_im; L[1 + h].rot_C = C; L[1 + h].rot_ch0 = h * 64;
+      L[1 + h].dots_src = pq + h * 64; L[1 + h].ld_dots = 2 * C; L[1 + h].dots_gy_col = C;
+    }
+    gf_tc = tc_rows_chain_supported(src_gxy, &L[1], 1, tc_passes(engine)) == DN_OK &&
+            tc_rows_chain_supported(src_gxy, &L[2], 1, tc_passes(engine)) == DN_OK;
+    if (gf_tc) nfront = 3;
+  }
+  if (p->with_gradient_features && !gf_tc) {
     if (rot && npq > 256) {
       // [P|Q] wider than one tensor-core layer (C_width = 256): P and Q are separate layers writing the two halves
       L[1] = make_layer(p->A_re, C, 0, nullptr, 0, C, C, pq, npq);
@@ -671,10 +696,12 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
   const int passes = tc_passes(engine);
   const bool front_fused = tc && nfront == 2 && tc_rows_chain_supported(src_fb, &L[0], 2, passes) == DN_OK;
   bool tc_front = front_fused;
+  const DnRowsSrc& src_l12 = gf_tc ? src_gxy : src_pq;      // input of L[1], L[2]: raw gradients | x_diffuse
   if (tc && !front_fused) {
     tc_front = tc_rows_chain_supported(src_fb, &L[0], 1, passes) == DN_OK;
-    for (int l = 1; l < nfront; ++l) tc_front = tc_front && tc_rows_chain_supported(src_pq, &L[l], 1, passes) == DN_OK;
+    for (int l = 1; l < nfront; ++l) tc_front = tc_front && tc_rows_chain_supported(src_l12, &L[l], 1, passes) == DN_OK;
   }
+  if (gf_tc && !tc_front) return DN_ERR_UNSUPPORTED;         // (from_basis outside the envelope: cannot happen at C = 128)
   const bool tc_mlp = tc && tc_rows_chain_supported(src_mlp, &L[nfront], nm, passes) == DN_OK;
   // the spectral multiplier S = exp(-lambda t) * (reduced partial sums) is layer 0's weight: when the tensor-core path
   // takes the front chain it is formed inside the pack launch (no separate scale kernel, S never round-trips HBM)
@@ -686,7 +713,7 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
     if (front_fused) tc_choose_pack_fmt(src_fb, &L[0], 2, passes);
     else {
       tc_choose_pack_fmt(src_fb, &L[0], 1, passes);
-      for (int l = 1; l < nfront; ++l) tc_choose_pack_fmt(src_pq, &L[l], 1, passes);
+      for (int l = 1; l < nfront; ++l) tc_choose_pack_fmt(src_l12, &L[l], 1, passes);
     }
   }
   if (tc_mlp) tc_choose_pack_fmt(src_mlp, &L[nfront], nm, passes);
@@ -731,13 +758,23 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
     if ((rc = run_chain(src_fb, &L[0], 2, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
   } else {
     if ((rc = run_chain(src_fb, &L[0], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
-    for (int l = 1; l < nfront; ++l)
-      if ((rc = run_chain(src_pq, &L[l], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
+    if (!gf_tc)
+      for (int l = 1; l < nfront; ++l)
+        if ((rc = run_chain(src_pq, &L[l], 1, V, engine, nullptr, nullptr, tcws, tcws_bytes, st))) return rc;
   }
   mark(4);
   // (a4+a5) sparse tangent gradient + complex inner product + tanh   [layers.py:216-226,128-130]
-  if (p->with_gradient_features)
+  if (gf_tc) {
+    if ((rc = launch_spmm_gxy(grad, xd, V, C, pq, st))) return rc;
+    if (ev) {
+      if (!g_gf_ev) cudaEventCreate(&g_gf_ev);
+      if (g_gf_ev) { cudaEventRecord(g_gf_ev, st); g_gf_recorded = true; }
+    }
+    for (int l = 1; l < nfront; ++l)
+      if ((rc = tc_rows_chain(src_gxy, &L[l], 1, V, passes, tcws, tcws_bytes, st))) return rc;
+  } else if (p->with_gradient_features) {
     if ((rc = launch_spmm_features(grad, xd, pq, rot, V, C, feat, st))) return rc;
+  }
   mark(5);
   rc = run_chain(src_mlp, &L[nfront], nm, V, engine, t0, t1, tcws, tcws_bytes, st);
   mark(6);
@@ -805,12 +842,15 @@ int dn_block_fwd_profile(const float* x_in, const float* mass, const float* eval
                          void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream, float* stage_ms_host) {
   if (!stage_ms_host) return DN_ERR_INVALID_ARGUMENT;
   cudaEvent_t ev[DN_PROFILE_STAGES + 1];
+  g_gf_recorded = false;
+  g_gf_gather_ms = 0.f;
   for (int i = 0; i <= DN_PROFILE_STAGES; ++i) DN_CUDA_TRY(cudaEventCreate(&ev[i]));
   int rc = block_fwd_impl(x_in, mass, evals, evecs, grad, p, V, K, C, out, workspace, ws_bytes, engine, stream, ev);
   if (rc == DN_OK) {
     rc = (int)cudaEventSynchronize(ev[DN_PROFILE_STAGES]);
     for (int i = 0; i < DN_PROFILE_STAGES && rc == DN_OK; ++i)
       rc = (int)cudaEventElapsedTime(&stage_ms_host[i], ev[i], ev[i + 1]);
+    if (rc == DN_OK && g_gf_recorded && cudaEventElapsedTime(&g_gf_gather_ms, ev[4], g_gf_ev) != cudaSuccess) cudaGetLastError();
   }
   for (int i = 0; i <= DN_PROFILE_STAGES; ++i) cudaEventDestroy(ev[i]);
   return rc;

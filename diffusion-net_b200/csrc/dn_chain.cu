@@ -61,7 +61,10 @@ struct C3Layer {
   int K, N, relu;
   int has_out;
   int has_res;             // 0: none | 1: + residual (layers.py:239) | 2: * (aux > 0): backward of ReLU, aux = the
-};                         //    forward activation (last layer only; the tensor is fetched through maps.res)
+                           //    forward activation (last layer only; the tensor is fetched through maps.res)
+                           // 3: complex inner product + tanh (layers.py:128-130): accumulator = [Bre | Bim], N/2 columns
+  int gy_col;              //    each; gX / gY boxes come through maps.res at columns c and gy_col + c; output N/2 wide
+};
 
 struct C3Params {
   C3Layer layer[DN_MAX_LAYERS];
@@ -72,7 +75,8 @@ struct C3Params {
   int nbuf;        // accumulator buffers (2: ping-pong, column 128 * (g & 1); 1: column 0)
   int ring_col;    // first TMEM column of the operand ring
   int ns_shift;    // log2(ring depth): 2 -> 4 stages (32 KiB weight slots), 1 -> 2 stages (64 KiB weight slots)
-  int nr_shift;    // log2(row-box slots): 2 or 1;  output staging buffers = 6 - slots
+  int nr_shift;    // log2(row-box slots): 2 or 1;  output staging buffers = nio - slots
+  int nio;         // 16 KiB row-box + staging buffers in front of the weight ring: 6 (weight ring 128 KiB) or 8 (96 KiB)
   int64_t V;
   long long* trace;   // optional (tools/trace_chain3.py): per-warp (event, clock64) pairs of CTA 0
   const int32_t* tile_group;   // optional (mesh batches): layer 0 of tile t streams the packed matrix number tile_group[t]
@@ -148,8 +152,8 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
   const uint32_t smem0 = smem_u32(smem);
   if (smem0 & 1023u) __trap();                                          // SWIZZLE_128B boxes need 1024 B alignment
   const uint32_t nr_sh = (uint32_t)p.nr_shift, nr_mask = (1u << nr_sh) - 1u;
-  const uint32_t nout = (uint32_t)C3_IO_BUFS - (1u << nr_sh), nout_mask = nout - 1u;   // 2 or 4
-  const uint32_t raw_u = smem0, out_u = smem0 + ((uint32_t)C3_RAW << nr_sh), w_u = smem0 + C3_OFF_W;
+  const uint32_t nout = (uint32_t)p.nio - (1u << nr_sh), nout_mask = nout - 1u;        // 2 or 4
+  const uint32_t raw_u = smem0, out_u = smem0 + ((uint32_t)C3_RAW << nr_sh), w_u = smem0 + (uint32_t)p.nio * C3_RAW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C3_OFF_BAR);
 
   // bars: raw_full[4] raw_empty[4] full[4] ab_empty[4] dm_full[2] do_full[2] dm_empty[2] do_empty[2] res[4 warps][2] done
@@ -195,7 +199,7 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
   const int64_t ntiles = (p.V + C3_TILE - 1) / C3_TILE;
   const int nst0 = p.layer[0].K / C3_KS;
   const uint32_t ns_sh = (uint32_t)p.ns_shift, ns_mask = (1u << ns_sh) - 1u;
-  const uint32_t w_slot = (uint32_t)C3_WBYTES >> ns_sh;       // 32 KiB or 64 KiB
+  const uint32_t w_slot = (((uint32_t)C3_OFF_BAR - (uint32_t)p.nio * C3_RAW) >> ns_sh) & ~1023u;   // 32 / 64 KiB (nio 6), 48 KiB (nio 8)
   const bool two = p.nbuf == 2;
 
   if (warp == 0) {
@@ -468,9 +472,73 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         const uint32_t use = buf ? uo1 : uo0;
         if (buf) ++uo1; else ++uo0;
         const int nco = Lr.N / C3_KS;
+        const uint32_t d_lane = lane_base + buf * 128u;
+        if (Lr.has_res == 3) {
+          // feat = tanh(gX * Bre + gY * Bim): per 32-channel chunk two accumulator reads and two TMA boxes (gX into
+          // this warp's slice of staging buffer 0, gY into buffer 1); the result overwrites slice 0 and is stored
+          const int half = Lr.N >> 1, nch = half / C3_KS;
+          const uint32_t slq = out_u + (uint32_t)quarter * 4096u;
+          // with four staging buffers (nio == 8) every gX / gY box of the tile is requested before the accumulator is
+          // awaited: the loads overlap the tile's MMAs instead of sitting between the accumulator and the store
+          const bool pre = (int)nout >= 2 * nch;
+          if (pre && lane == 0) {
+            bulk_wait_read<0>();                                 // the previous tile's stores have left the slices
+            for (int c = 0; c < nch; ++c) {
+              mbar_arrive_expect_tx(my_res + 16 * c, 4096);
+              tma_box_load(slq + (uint32_t)(2 * c) * C3_RAW, &maps.res, c * C3_KS, row0, my_res + 16 * c);
+              mbar_arrive_expect_tx(my_res + 16 * c + 8, 4096);
+              tma_box_load(slq + (uint32_t)(2 * c + 1) * C3_RAW, &maps.res, Lr.gy_col + c * C3_KS, row0, my_res + 16 * c + 8);
+            }
+          }
+          __syncwarp();
+          mbar_wait(do_full + 8 * buf, use & 1u);
+          tc_fence_after();
+          for (int c = 0; c < nch; ++c) {
+            const int sb = pre ? 2 * c : 0;                      // staging buffers of this chunk: sb (gX, result), sb + 1 (gY)
+            const uint32_t sl0 = slq + (uint32_t)sb * C3_RAW, sl1 = sl0 + C3_RAW;
+            if (!pre) {
+              if (lane == 0) {
+                bulk_wait_read<0>();
+                mbar_arrive_expect_tx(my_res, 4096);
+                tma_box_load(sl0, &maps.res, c * C3_KS, row0, my_res);
+                mbar_arrive_expect_tx(my_res + 8, 4096);
+                tma_box_load(sl1, &maps.res, Lr.gy_col + c * C3_KS, row0, my_res + 8);
+              }
+              __syncwarp();
+            }
+            float re[32], im[32];
+            tmem_ld32(d_lane + (uint32_t)c * C3_KS, re);
+            tmem_ld32(d_lane + (uint32_t)(half + c * C3_KS), im);
+            if (c + 1 == nch) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(do_empty + 8 * buf);
+            }
+            mbar_wait(my_res + 8 * sb, (rcbits >> sb) & 1u);
+            mbar_wait(my_res + 8 * sb + 8, (rcbits >> (sb + 1)) & 1u);
+            rcbits ^= (3u << sb);
+            const uint32_t r0 = sl0 + (uint32_t)lane * 128u, r1 = sl1 + (uint32_t)lane * 128u;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const uint32_t o = (((uint32_t)jj) ^ swz) << 4;
+              const float4 gx = lds128(r0 + o), gy = lds128(r1 + o);
+              sts128(r0 + o, dn_feat_tanh(fmaf(gx.x, re[4 * jj], gy.x * im[4 * jj])),
+                     dn_feat_tanh(fmaf(gx.y, re[4 * jj + 1], gy.y * im[4 * jj + 1])),
+                     dn_feat_tanh(fmaf(gx.z, re[4 * jj + 2], gy.z * im[4 * jj + 2])),
+                     dn_feat_tanh(fmaf(gx.w, re[4 * jj + 3], gy.w * im[4 * jj + 3])));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_box_store(&maps.out[l], c * C3_KS, row0, sl0);
+              bulk_commit();
+            }
+            __syncwarp();
+          }
+          continue;
+        }
         const bool res = Lr.has_res != 0;
         const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
-        const uint32_t d_lane = lane_base + buf * 128u;
         float bl[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // bias lane of each chunk (N <= 256)
         if (Lr.bias) {
 #pragma unroll
@@ -647,6 +715,9 @@ int tc_chain3_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layer
       return DN_ERR_UNSUPPORTED;
     if (L.bias && (reinterpret_cast<uintptr_t>(L.bias) & 15)) return DN_ERR_UNSUPPORTED;
     if (!last && (L.residual || L.row_scale)) return DN_ERR_UNSUPPORTED;
+    if (L.dots_src && (!last || L.residual || L.relu_mask_src || L.row_scale || L.bias || L.relu || (L.N % 64) || L.N > 128 ||
+                       (L.ld_dots % 4) || (L.dots_gy_col % 4) || (reinterpret_cast<uintptr_t>(L.dots_src) & 15)))
+      return DN_ERR_UNSUPPORTED;
     if (!last && L.N % 64) return DN_ERR_UNSUPPORTED;             // it is the next layer's K
     if (L.residual && (L.res_scale != 1.f || L.ld_res % 4 || (reinterpret_cast<uintptr_t>(L.residual) & 15)))
       return DN_ERR_UNSUPPORTED;
@@ -701,7 +772,14 @@ int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, in
     if (!L.prepacked) return DN_ERR_INVALID_ARGUMENT;
     T.wpack = L.prepacked; T.bias = L.bias; T.row_scale = L.row_scale; T.K = L.K; T.N = L.N; T.relu = L.relu;
     T.has_out = L.out != nullptr;
-    T.has_res = L.residual ? 1 : (L.relu_mask_src ? 2 : 0);
+    T.has_res = L.residual ? 1 : (L.relu_mask_src ? 2 : (L.dots_src ? 3 : 0));
+    T.gy_col = L.dots_gy_col;
+    if (L.dots_src) {     // output is N/2 wide; gX / gY boxes come from dots_src (any width >= gy_col + N/2)
+      if (!L.out || make_box_map(&maps.out[l], L.out, L.N / 2, L.ld_out, V, 32)) return DN_ERR_UNSUPPORTED;
+      if (make_box_map(&maps.res, L.dots_src, L.dots_gy_col + L.N / 2, L.ld_dots, V, 32)) return DN_ERR_UNSUPPORTED;
+      if (L.N > nmax) nmax = L.N;
+      continue;
+    }
     if (L.out && make_box_map(&maps.out[l], L.out, L.N, L.ld_out, V, 32)) return DN_ERR_UNSUPPORTED;
     if (L.residual && make_box_map(&maps.res, L.residual, L.N, L.ld_res, V, 32)) return DN_ERR_UNSUPPORTED;
     if (L.relu_mask_src && make_box_map(&maps.res, L.relu_mask_src, L.N, L.N, V, 32)) return DN_ERR_UNSUPPORTED;
@@ -714,6 +792,11 @@ int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, in
   // (measured on the from_basis -> [P|Q] chain: 2 + 4 was SLOWER, 124 vs 108 us -- the extra staging traffic competes
   //  with the tensor core for shared-memory bandwidth -- so 4 + 2 stays the default; DN_C3_NR=2 selects 2 + 4)
   p.nr_shift = 2;
+  p.nio = C3_IO_BUFS;
+  if (n_layers == 1 && layers[0].dots_src && nmax <= 128) {
+    // complex-dots layer: 4 row boxes + 4 staging buffers (all gX / gY boxes of a tile prefetched) + a 2-stage ring
+    p.nio = 8; p.ns_shift = 1;
+  }
   {
     static int nr_env = -2;
     if (nr_env == -2) { const char* e = getenv("DN_C3_NR"); nr_env = e ? atoi(e) : -1; }

@@ -51,7 +51,24 @@ struct DnLayer {
   // and 128-row tile t uses matrix tile_group[t] (device array)
   const int32_t* tile_group;
   int64_t group_stride;
+  // complex inner-product epilogue (last layer of a chain only; layers.py:128-130).  The layer computes
+  // [Bre | Bim] = in @ W^T with N/2 columns each for N/2 channels; the output (N/2 wide) is
+  //   tanh(gX * Bre + gY * Bim),  gX = dots_src[:, c], gY = dots_src[:, dots_gy_col + c]   (row stride ld_dots)
+  const float* dots_src;
+  int64_t ld_dots;
+  int dots_gy_col;
+  // weights given as the pair (W = A_re, W2 = A_im) of SpatialGradientFeatures acting on [gX | gY]: see PackJob::rot_C
+  int rot_C, rot_ch0;
 };
+
+#ifdef __CUDACC__
+// tanh of the gradient features (layers.py:130): 1 - 2 / (exp(2x) + 1) with the fast exp / divide; absolute error
+// <= ~1.5e-7 over the whole range, saturates to +-1, NaN propagates.  Every kernel that forms features uses this one.
+__device__ __forceinline__ float dn_feat_tanh(float x) {
+  const float e = __expf(2.f * x);
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+#endif
 
 struct DnRowsSrc {
   const float* ptr[DN_MAX_SRC];
@@ -88,6 +105,9 @@ int launch_grad_spmm_pair(const dn_csr* g, const float* x, int64_t V, int C, flo
 // R-order fused features: feat = tanh(gX*Bre + gY*Bim) from gathers of xd, P, Q (pq = [P|Q], ld 2C or C).
 int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int rotations, int64_t V, int C,
                          float* feat, cudaStream_t st);
+// gxy[v] = [ (gradX @ x)[v] | (gradY @ x)[v] ]  (V x 2C, row-major): the gather of the tensor-core gradient-features
+// route (C = 128 or 256)
+int launch_spmm_gxy(const dn_csr* g, const float* x, int64_t V, int C, float* gxy, cudaStream_t st);
 int launch_features_bwd_local(const dn_csr* g, const float* xd, const float* pq, const float* feat,
                               const float* dfeat, int rotations, int64_t V, int C, float* U /*V x 4C*/,
                               cudaStream_t st);

@@ -360,10 +360,7 @@ struct Acc4 {
 // (the gather kernel issues instructions on 53 % of its cycles, profiles/r01: the four tanhf per lane were a fifth of
 // them).  Absolute error <= ~1.5e-7 over the whole range (saturates to +-1, NaN propagates); every gather variant
 // uses this one function so that they stay bit-identical to each other.
-__device__ __forceinline__ float feat_tanh(float x) {
-  const float e = __expf(2.f * x);
-  return 1.f - __fdividef(2.f, e + 1.f);
-}
+__device__ __forceinline__ float feat_tanh(float x) { return dn_feat_tanh(x); }
 
 template <bool ROT>
 __device__ __forceinline__ Acc4 gather_row(const int32_t* __restrict__ colidx, const float2* __restrict__ vals,
@@ -527,6 +524,95 @@ spmm_features_blk_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
     *reinterpret_cast<float4*>(feat + (base + r) * C + h * 128 + lane * 4) = o;
   }
 }
+
+// The same block gather for the tensor-core gradient-features route: only x_diffuse is gathered (7 x 512 B per
+// vertex instead of 7 x 1.5 KB) and the raw tangent gradients are written out,
+//     gxy[v] = [ sum_j gx_vj x_j | sum_j gy_vj x_j ]                                       (layers.py:216-223)
+// the complex-linear map, the inner product and the tanh follow as a tcgen05 GEMM with a fused epilogue (rows_chain3,
+// has_res == 3).  Entry order = CSR order, fmaf per element (as FFMA2).
+struct __align__(16) GxyEnt { int col; float gx, gy; int pad; };
+
+// One CSR entry of the x-only gather: the neighbour row's 16-byte slice is loaded, then 4 FFMA2 -- gX += gx * x, gY += gy * x
+#define DN_GXY_LOAD(J, ENT)                                                                          \
+  const int4 en##J = *reinterpret_cast<const int4*>(&(ENT));                                         \
+  const ulonglong2 x##J = __ldg(reinterpret_cast<const ulonglong2*>(xb + (int64_t)en##J.x * x_row_bytes));
+#define DN_GXY_FMA(J)                                                                                \
+  {                                                                                                  \
+    const float wx = __int_as_float(en##J.y), wy = __int_as_float(en##J.z);                          \
+    const unsigned long long gx2 = pack2(wx, wx), gy2 = pack2(wy, wy);                               \
+    fma2(gX0, gx2, x##J.x); fma2(gX1, gx2, x##J.y);                                                  \
+    fma2(gY0, gy2, x##J.x); fma2(gY1, gy2, x##J.y);                                                  \
+  }
+
+// The instruction count is what bounds this kernel (ncu: 71 % issue-active in the first version, whose per-entry
+// predicates and two staging arrays cost ~4x the useful instructions): entries are staged as 16-byte records (one
+// broadcast LDS.128 per entry), full batches of 7 run without predicates, and blocks whose entries do not fit the
+// staging buffer take a separate (generic) path.
+template <int NH>
+__global__ void __launch_bounds__(256, 3)
+spmm_gxy_blk_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                    const float2* __restrict__ vals, const float* __restrict__ xd, int64_t V, float* __restrict__ gxy) {
+  constexpr int C = 128 * NH;
+  constexpr int64_t x_row_bytes = (int64_t)C * 4;
+  __shared__ int s_rp[GB_ROWS + 1];
+  __shared__ GxyEnt s_e[GB_NNZ];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = (int64_t)blockIdx.x * GB_ROWS;
+  const int nrows = (int)((V - base) < GB_ROWS ? (V - base) : GB_ROWS);
+  if ((int)threadIdx.x <= nrows) s_rp[threadIdx.x] = __ldg(rowptr + base + threadIdx.x);
+  __syncthreads();
+  const int e0 = s_rp[0];
+  const int tot = s_rp[nrows] - e0;
+  const bool staged = tot <= GB_NNZ;                              // (block-uniform)
+  if (staged) {
+    for (int i = threadIdx.x; i < tot; i += 256) {
+      const float2 g = __ldg(vals + e0 + i);
+      GxyEnt en;
+      en.col = __ldg(colidx + e0 + i); en.gx = g.x; en.gy = g.y; en.pad = 0;
+      s_e[i] = en;
+    }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int rh = warp; rh < nrows * NH; rh += 8) {
+    const int r = rh / NH, h = rh % NH;
+    const char* xb = reinterpret_cast<const char*>(xd) + h * 512 + lane * 16;
+    const int s = s_rp[r] - e0, e = s_rp[r + 1] - e0;
+    unsigned long long gX0 = 0ull, gX1 = 0ull, gY0 = 0ull, gY1 = 0ull;
+    if (staged) {
+      int p = s;
+#pragma unroll 1
+      for (; p + 7 <= e; p += 7) {                                // full batches: seven independent loads, no predicates
+        DN_GXY_LOAD(0, s_e[p]) DN_GXY_LOAD(1, s_e[p + 1]) DN_GXY_LOAD(2, s_e[p + 2]) DN_GXY_LOAD(3, s_e[p + 3])
+        DN_GXY_LOAD(4, s_e[p + 4]) DN_GXY_LOAD(5, s_e[p + 5]) DN_GXY_LOAD(6, s_e[p + 6])
+        DN_GXY_FMA(0) DN_GXY_FMA(1) DN_GXY_FMA(2) DN_GXY_FMA(3) DN_GXY_FMA(4) DN_GXY_FMA(5) DN_GXY_FMA(6)
+      }
+#pragma unroll 1
+      for (; p + 2 <= e; p += 2) {                                // remainder: pairs, then a single entry
+        DN_GXY_LOAD(0, s_e[p]) DN_GXY_LOAD(1, s_e[p + 1])
+        DN_GXY_FMA(0) DN_GXY_FMA(1)
+      }
+      if (p < e) {
+        DN_GXY_LOAD(0, s_e[p])
+        DN_GXY_FMA(0)
+      }
+    } else {
+#pragma unroll 1
+      for (int p = s; p < e; ++p) {                               // (a block with more than GB_NNZ entries)
+        GxyEnt en;
+        const float2 g = __ldg(vals + e0 + p);
+        en.col = __ldg(colidx + e0 + p); en.gx = g.x; en.gy = g.y; en.pad = 0;
+        DN_GXY_LOAD(0, en)
+        DN_GXY_FMA(0)
+      }
+    }
+    char* o = reinterpret_cast<char*>(gxy + (base + r) * (2 * C)) + h * 512 + lane * 16;
+    *reinterpret_cast<ulonglong2*>(o) = make_ulonglong2(gX0, gX1);
+    *reinterpret_cast<ulonglong2*>(o + x_row_bytes) = make_ulonglong2(gY0, gY1);
+  }
+}
+#undef DN_GXY_LOAD
+#undef DN_GXY_FMA
 
 // Patch variant (dn_patches, built once for resident operators): one CTA per patch of graph-adjacent rows.
 // Phase 1 copies the patch's distinct neighbour rows of x_diffuse and [P|Q] into shared memory, coalesced, each row
@@ -898,6 +984,18 @@ int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int 
     spmm_features_kernel<true><<<blocks, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, 2 * C, V, C, G, feat);
   else
     spmm_features_kernel<false><<<blocks, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, C, V, C, G, feat);
+  DN_LAUNCH_CHECK();
+  return DN_OK;
+}
+
+int launch_spmm_gxy(const dn_csr* g, const float* x, int64_t V, int C, float* gxy, cudaStream_t st) {
+  if (V <= 0) return DN_OK;
+  if (C != 128 && C != 256) return DN_ERR_UNSUPPORTED;
+  const float2* vals = reinterpret_cast<const float2*>(g->vals);
+  const unsigned ctas = (unsigned)((V + GB_ROWS - 1) / GB_ROWS);
+  // (measured, tools/gf_check.py: streaming stores change nothing, 4 CTAs / SM with 64 registers is 5 % slower)
+  if (C == 128) spmm_gxy_blk_kernel<1><<<ctas, 256, 0, st>>>(g->rowptr, g->colidx, vals, x, V, gxy);
+  else spmm_gxy_blk_kernel<2><<<ctas, 256, 0, st>>>(g->rowptr, g->colidx, vals, x, V, gxy);
   DN_LAUNCH_CHECK();
   return DN_OK;
 }

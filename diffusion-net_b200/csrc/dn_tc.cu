@@ -69,6 +69,10 @@ struct PackJob {
   float* dst;
   int64_t ldw;
   int n_split, w_trans, K, N, blk0, fmt;
+  // rot_C > 0: the matrix is the complex-linear map of SpatialGradientFeatures (layers.py:121-123) applied to
+  // [gX | gY] (K = 2 * rot_C) for channels [rot_ch0, rot_ch0 + N/2):  rows n < N/2 give Bre = A_re gX - A_im gY, rows
+  // n >= N/2 give Bim = A_im gX + A_re gY   (W = A_re, W2 = A_im, both (rot_C, rot_C) with row stride ldw)
+  int rot_C, rot_ch0;
 };
 struct PackJobs {
   PackJob j[DN_MAX_LAYERS];
@@ -148,7 +152,13 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackJobs jobs) {
     const int idx = ((int)blockIdx.x - J.blk0) * blockDim.x + threadIdx.x;
     if (idx >= K * N) return;
     n = idx / K; k = idx % K;
-    if (J.w_trans) w = (J.W2 && k >= J.n_split) ? J.W2[(int64_t)(k - J.n_split) * J.ldw + n] : J.W[(int64_t)k * J.ldw + n];
+    if (J.rot_C > 0) {
+      const int nh = N >> 1, Cc = J.rot_C;
+      const bool im = n >= nh;
+      const int64_t ch = J.rot_ch0 + (im ? n - nh : n);
+      if (k < Cc) w = im ? J.W2[ch * J.ldw + k] : J.W[ch * J.ldw + k];
+      else w = im ? J.W[ch * J.ldw + (k - Cc)] : -J.W2[ch * J.ldw + (k - Cc)];
+    } else if (J.w_trans) w = (J.W2 && k >= J.n_split) ? J.W2[(int64_t)(k - J.n_split) * J.ldw + n] : J.W[(int64_t)k * J.ldw + n];
     else if (J.W2 && n >= J.n_split) w = J.W2[(int64_t)(n - J.n_split) * J.ldw + k];
     else w = J.W[(int64_t)n * J.ldw + k];
   }
@@ -1166,7 +1176,7 @@ static int tc_rows_chain_legacy_supported(const DnRowsSrc& src, const DnLayer* l
   for (int l = 0; l < n_layers; ++l) {
     const DnLayer& L = layers[l];
     if (L.K % 16 || L.K < 16 || L.N % 16 || L.N < 16 || L.N > 256) return DN_ERR_UNSUPPORTED;
-    if (L.emul || L.relu_mask_src) return DN_ERR_UNSUPPORTED;
+    if (L.emul || L.relu_mask_src || L.dots_src) return DN_ERR_UNSUPPORTED;
     if (L.bias && (reinterpret_cast<uintptr_t>(L.bias) & 15)) return DN_ERR_UNSUPPORTED;
     if (L.residual && (L.res_scale != 1.f || L.ld_res % 4 || (reinterpret_cast<uintptr_t>(L.residual) & 15)))
       return DN_ERR_UNSUPPORTED;
@@ -1228,6 +1238,7 @@ int tc_pack_layers_spectral(DnLayer* layers, int n_layers, void* ws, int64_t ws_
     PackJob& J = jobs.j[l];
     J.W = L.W; J.W2 = L.W2; J.n_split = L.n_split; J.ldw = L.ldw; J.w_trans = L.w_trans; J.K = L.K; J.N = L.N;
     J.fmt = L.pack_fmt;
+    J.rot_C = L.rot_C; J.rot_ch0 = L.rot_ch0;
     J.dst = reinterpret_cast<float*>(wp);
     J.blk0 = blocks;
     blocks += (l == 0 && partial) ? (L.K * L.N + 31) / 32 : (L.K * L.N + 255) / 256;
