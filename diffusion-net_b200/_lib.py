@@ -98,6 +98,7 @@ SIGNATURES = {
                           _I, _P]),
     "dn_block_fwd_profile": (_I, [_P, _P, _P, _P, C.POINTER(dn_csr), C.POINTER(dn_block_params), _L, _I, _I, _P, _P, _L,
                                   _I, _P, C.POINTER(C.c_float)]),
+    "dn_build_grad": (_I, [_P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _L, _P]),
     "dn_mesh_batch_plan": (_I, [_I, _P, _I, _P, _P, _P, _P]),
     "dn_block_fwd_batched": (_I, [_P, _P, _P, _P, C.POINTER(dn_csr), C.POINTER(dn_block_params), C.POINTER(dn_mesh_batch),
                                   _L, _I, _I, _P, _P, _L, _I, _P]),

@@ -282,6 +282,18 @@ int dn_csr_transpose(const dn_csr* in, int64_t V, int32_t* rowptr_out, int32_t* 
   return launch_csr_transpose(in, V, rowptr_out, colidx_out, vals_out, (int32_t*)workspace, (cudaStream_t)stream);
 }
 
+int dn_build_grad(const float* verts, const float* frames, const float* edge_tangent, const int64_t* edges, int64_t E,
+                  int64_t V, int32_t* rowptr_out, int32_t* colidx_out, float* vals_out, void* workspace, int64_t ws_bytes,
+                  dn_stream_t stream) {
+  if (V < 0 || E < 0 || !rowptr_out || (V > 0 && (!colidx_out || !vals_out)) || (E > 0 && !edges) ||
+      (E > 0 && !edge_tangent && (!verts || !frames)))
+    return DN_ERR_INVALID_ARGUMENT;
+  if (E + V >= (1ll << 31) || V >= (1ll << 31) - 1) return DN_ERR_UNSUPPORTED;
+  if (V > 0 && (!workspace || ws_bytes < (int64_t)sizeof(int32_t) * V)) return DN_ERR_WORKSPACE;
+  return launch_build_grad(verts, frames, edge_tangent, edges, E, V, rowptr_out, colidx_out, vals_out, (int32_t*)workspace,
+                           (cudaStream_t)stream);
+}
+
 int dn_compute_hks(const float* evals, const float* evecs, const float* scales, int64_t V, int K, int S, float* out,
                    dn_stream_t stream) {
   if (V < 0 || K <= 0 || S < 0 || ((V > 0 && S > 0) && (!evals || !evecs || !scales || !out)))

@@ -99,6 +99,8 @@ int launch_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* v
                         int64_t nnz, int64_t V, int32_t* rowptr, int32_t* colidx, float* vals, cudaStream_t st);
 int launch_compute_hks(const float* evals, const float* evecs, const float* scales, int64_t V, int K, int S,
                        float* out, cudaStream_t st);
+int launch_build_grad(const float* verts, const float* frames, const float* edge_tangent, const int64_t* edges, int64_t E,
+                      int64_t V, int32_t* rowptr, int32_t* colidx, float* vals, int32_t* cursor, cudaStream_t st);
 int launch_csr_transpose(const dn_csr* in, int64_t V, int32_t* rowptr_t, int32_t* colidx_t, float* vals_t,
                          int32_t* cursor, cudaStream_t st);
 int launch_grad_spmm_pair(const dn_csr* g, const float* x, int64_t V, int C, float* out_vc2, cudaStream_t st);

@@ -149,3 +149,57 @@ def get_all_operators(verts_list, faces_list, k_eig, op_cache_dir=None, normals=
     """geometry.py:395-424: seven parallel lists."""
     outs = [get_operators(v, f, k_eig, op_cache_dir, device=device) for v, f in zip(verts_list, faces_list)]
     return tuple([o[i] for o in outs] for i in range(7))
+
+
+# ------------------------------------------------------------------------------------------------
+# operator construction, per-vertex part (SURVEY.md 8f-4): the reference's pure-Python build_grad loop on the device
+# ------------------------------------------------------------------------------------------------
+def edge_tangent_vectors(verts, frames, edges):
+    """Reference geometry.py:198-207 (plain torch ops, any device): (E,2) tangent-plane coordinates of every edge."""
+    edge_vecs = verts[edges[1, :], :] - verts[edges[0, :], :]
+    basisX = frames[edges[0, :], 0, :]
+    basisY = frames[edges[0, :], 1, :]
+    return torch.stack(((edge_vecs * basisX).sum(-1), (edge_vecs * basisY).sum(-1)), dim=-1)
+
+
+def build_grad_operators(verts, frames, edges, edge_tangent=None):
+    """``edge_tangent_vectors`` + ``build_grad`` (reference geometry.py:198-273) on the GPU, straight into the prepared
+    shared-pattern CSR the layers consume: returns ``ops.GradOperators`` standing for the (gradX, gradY) pair
+    (``.to_sparse_coo()`` gives the two coalesced COO tensors the reference returns).  ``edges``: (2,E) integer tensor
+    as in the reference (for meshes: the Laplacian's sparsity pattern, geometry.py:374-376).  One host sync (the entry
+    count); fp64 2x2 solves like numpy; 1e-6-grade agreement with the reference (tests/test_gpu_parity.py)."""
+    import ctypes as C
+    from . import _lib
+    ops._require_cuda(verts)
+    dev = verts.device
+    V = int(verts.shape[0])
+    edges = edges.to(device=dev, dtype=torch.int64).contiguous()
+    E = int(edges.shape[1])
+    verts = verts.to(torch.float32).contiguous()
+    frames = frames.to(device=dev, dtype=torch.float32).contiguous()
+    et = None if edge_tangent is None else edge_tangent.to(device=dev, dtype=torch.float32).contiguous()
+    rowptr = torch.empty(V + 1, dtype=torch.int32, device=dev)
+    colidx = torch.empty(max(E + V, 1), dtype=torch.int32, device=dev)
+    vals = torch.empty(max(E + V, 1), 2, dtype=torch.float32, device=dev)
+    ws = torch.empty(max(4 * V, 4), dtype=torch.uint8, device=dev)
+    with ops._on(verts):
+        _lib.check(_lib.load().dn_build_grad(verts.data_ptr(), frames.data_ptr(), et.data_ptr() if et is not None else None,
+                                             edges.data_ptr(), E, V, rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), ops._stream()), "dn_build_grad")
+    nnz = int(rowptr[-1].item()) if V > 0 else 0
+    return ops.GradOperators.from_csr(V, rowptr, colidx[:max(nnz, 1)] if nnz else colidx[:0], vals[:nnz])
+
+
+def build_grad(verts, edges, edge_tangent_vectors):
+    """Drop-in for the reference's ``build_grad`` (geometry.py:209-273): numpy / torch in, scipy complex CSC (V,V) out,
+    computed by ``dn_build_grad`` on the current CUDA device instead of the per-vertex Python loop."""
+    import scipy.sparse
+    dev = torch.device("cuda", torch.cuda.current_device())
+    V = int(verts.shape[0])
+    as_t = lambda a, dt: (a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))).to(device=dev, dtype=dt)
+    g = build_grad_operators(torch.empty(V, 3, device=dev), torch.empty(V, 3, 3, device=dev), as_t(edges, torch.int64),
+                             edge_tangent=as_t(edge_tangent_vectors, torch.float32))
+    rowptr, colidx, vals = g.to_host_csr()
+    vals = np.asarray(vals, dtype=np.float64)
+    data = vals[:, 0] + 1j * vals[:, 1]
+    return scipy.sparse.csr_matrix((data, np.asarray(colidx), np.asarray(rowptr)), shape=(V, V)).tocsc()

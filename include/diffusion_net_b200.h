@@ -224,6 +224,16 @@ int dn_block_fwd_profile(const float* x_in, const float* mass, const float* eval
                          float* out, void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream,
                          float* stage_ms_host);
 
+/* Operator construction, the per-vertex part: geometry.py:198-207 `edge_tangent_vectors` +
+ * geometry.py:209-273 `build_grad` on the device, straight into dn_csr arrays.  `edges` is the reference's (2, E) int64
+ * tensor (row 0 tails, row 1 tips, any order; self loops are skipped as in :228).  Pass either `edge_tangent` (E, 2)
+ * as `build_grad` receives it, or NULL with `verts` (V, 3) and `frames` (V, 3, 3) to have it computed.  Row v of the
+ * result holds the entry of v itself followed / surrounded by its neighbours, columns sorted; capacity E + V entries,
+ * the actual count is rowptr_out[V] (device).  fp64 2x2 solves like numpy.  workspace: 4 * V bytes. */
+int dn_build_grad(const float* verts, const float* frames, const float* edge_tangent, const int64_t* edges, int64_t E,
+                  int64_t V, int32_t* rowptr_out, int32_t* colidx_out, float* vals_out, void* workspace,
+                  int64_t ws_bytes, dn_stream_t stream);
+
 /* ---- batches of independent meshes in one launch sequence (BASELINE config 4) -------------------
  * The reference loops over the batch dimension with one set of operators per mesh (layers.py:217-222; a DataLoader
  * of batch_size None in every experiment).  Here a batch is ONE vertex range: mesh b occupies rows

@@ -209,3 +209,34 @@ def read_operator_cache(npz, k_eig):
                              shape=shape).tocsr()
     return (npz["frames"], npz["mass"], mat("L"), npz["evals"][:k_eig], npz["evecs"][:, :k_eig],
             mat("gradX"), mat("gradY"))
+
+
+def edge_tangent_vectors(verts, frames, edges):
+    """geometry.py:198-207: tangent-plane coordinates of every edge vector in the frame of its tail vertex.
+    verts (V,3), frames (V,3,3) with rows (basisX, basisY, normal), edges (2,E) -> (E,2), in verts' dtype."""
+    edge_vecs = verts[edges[1]] - verts[edges[0]]
+    bx, by = frames[edges[0], 0, :], frames[edges[0], 1, :]
+    return np.stack(((edge_vecs * bx).sum(-1), (edge_vecs * by).sum(-1)), axis=-1)
+
+
+def build_grad(n_verts, edges, edge_tangent):
+    """geometry.py:209-273: per vertex, the least-squares gradient of a scalar from its outgoing edges,
+    ``(lhs^T lhs + 1e-5 I)^-1 lhs^T`` applied to value differences; row v of the result holds the complex coefficient of
+    v itself (minus the sum of the others) and of every neighbour.  fp64 like the reference (np.zeros / np.linalg.inv).
+    Returns scipy CSR complex128 (V,V); duplicate (row, col) pairs are summed as coo_matrix -> tocsc() does."""
+    edges = np.asarray(edges)
+    et = np.asarray(edge_tangent, dtype=np.float64)
+    keep = edges[0] != edges[1]                                                # :228 (self loops are skipped)
+    tail, tip, et = edges[0][keep], edges[1][keep], et[keep]
+    order = np.argsort(tail, kind="stable")                                    # outgoing lists in edge order (:224-229)
+    tail, tip, et = tail[order], tip[order], et[order]
+    start = np.searchsorted(tail, np.arange(n_verts + 1))
+    rows, cols, vals = [], [], []
+    for v in range(n_verts):
+        lhs = et[start[v]:start[v + 1]]                                        # (n,2)  :245-252
+        inv = np.linalg.inv(lhs.T @ lhs + 1e-5 * np.identity(2)) @ lhs.T       # :255-256  (2,n)
+        coef = inv[0] + 1j * inv[1]                                            # :258-259: column i+1 of sol_mat
+        rows += [v] * (len(lhs) + 1)
+        cols += [v] + list(tip[start[v]:start[v + 1]])
+        vals += [-coef.sum()] + list(coef)                                     # column 0: rhs_mat[:,0] = -1
+    return sp.coo_matrix((np.array(vals), (np.array(rows), np.array(cols))), shape=(n_verts, n_verts)).tocsr()

@@ -437,6 +437,51 @@ def test_forward_batch_equals_per_mesh(dn, engine, C):
         dn.set_engine("tc3x")
 
 
+def test_build_grad_on_device_vs_reference(dn):
+    """dn_build_grad (edge_tangent_vectors + build_grad, geometry.py:198-273) against the gradX / gradY the
+    live reference produced (tests/golden/geom_small.npz) and against the oracle restatement on a larger mesh."""
+    import scipy.sparse as sp
+    fx = load_golden("geom_small")
+    V = fx["verts"].shape[0]
+    edges = torch.from_numpy(np.stack((fx["L_rows"], fx["L_cols"])).astype(np.int64))
+    g = dn.geometry.build_grad_operators(dev(fx["verts"]), dev(fx["frames"]), edges)
+    rowptr, colidx, vals = (np.asarray(a) for a in g.to_host_csr())
+    for k, name in enumerate(("gradX", "gradY")):
+        ref = sp.coo_matrix((fx[name + "_vals"], (fx[name + "_rows"], fx[name + "_cols"])), shape=(V, V)).tocsr()
+        ref.sort_indices()
+        assert np.array_equal(rowptr, ref.indptr) and np.array_equal(colidx, ref.indices)
+        assert np.abs(vals[:, k] - ref.data).max() <= 2e-6 * np.abs(ref.data).max()
+    # the reference-signature mirror (numpy in, scipy complex CSC out) with precomputed tangent vectors
+    et = O.edge_tangent_vectors(fx["verts"], fx["frames"], edges.numpy())
+    M = dn.geometry.build_grad(fx["verts"], edges.numpy(), et).tocsr()
+    M.sort_indices()
+    assert np.array_equal(M.indices, colidx) and np.abs(np.real(M.data) - vals[:, 0]).max() <= 1e-6 * np.abs(vals).max()
+    # a larger, irregular case: random frames / neighbour lists of varying length (incl. a vertex with no edges, a self
+    # loop, unsorted edge order) vs the fp64 oracle
+    rng = np.random.RandomState(3)
+    V2 = 5000
+    verts = rng.randn(V2, 3).astype(np.float32)
+    q = np.linalg.qr(rng.randn(V2, 3, 3))[0].astype(np.float32)
+    tails = np.repeat(np.arange(1, V2), rng.randint(3, 12, V2 - 1))          # vertex 0 has no outgoing edge
+    tips = rng.randint(0, V2, tails.shape[0])
+    keep = np.ones(tails.shape[0], bool)
+    seen = set()
+    for i, (a, b) in enumerate(zip(tails, tips)):                            # unique (tail, tip) pairs
+        keep[i] = (a, b) not in seen
+        seen.add((a, b))
+    e2 = np.stack((tails[keep], tips[keep]))
+    e2 = e2[:, rng.permutation(e2.shape[1])]
+    e2[1, 7] = e2[0, 7]                                                      # one self loop: skipped (geometry.py:228)
+    g2 = dn.geometry.build_grad_operators(dev(verts), dev(q), torch.from_numpy(e2))
+    rp2, ci2, va2 = (np.asarray(a) for a in g2.to_host_csr())
+    gold = O.build_grad(V2, e2, O.edge_tangent_vectors(verts, q, e2))     # fp32 tangent vectors like the torch ops
+    gold.sum_duplicates(); gold.sort_indices()
+    assert np.array_equal(rp2, gold.indptr) and np.array_equal(ci2, gold.indices)
+    scale = np.abs(gold.data).max()
+    assert np.abs(va2[:, 0] - np.real(gold.data)).max() <= 2e-5 * scale
+    assert np.abs(va2[:, 1] - np.imag(gold.data)).max() <= 2e-5 * scale
+
+
 def test_graphed_net_and_streamed_forward(dn):
     """CUDA-graph replay (launch-bound small meshes) and the host-streaming helper reproduce the eager forward."""
     dn.set_engine("tc3x")

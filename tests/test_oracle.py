@@ -142,3 +142,21 @@ def test_operator_cache_reader_matches_reference_hit_branch():
         want.sort_indices()
         assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices), pre
         assert np.array_equal(got.data, want.data), pre
+
+
+def test_build_grad_matches_reference_fixture():
+    """oracle.build_grad / edge_tangent_vectors (geometry.py:198-273) against gradX / gradY the live reference produced
+    for tests/golden/geom_small.npz (edges = the Laplacian's pattern, geometry.py:333-335, 374-376)."""
+    import scipy.sparse as sp
+    fx = load_golden("geom_small")
+    V = fx["verts"].shape[0]
+    edges = np.stack((fx["L_rows"], fx["L_cols"])).astype(np.int64)
+    et = O.edge_tangent_vectors(fx["verts"], fx["frames"], edges)
+    G = O.build_grad(V, edges, et).tocsr()
+    G.sum_duplicates(); G.sort_indices()
+    for name, part in (("gradX", np.real), ("gradY", np.imag)):
+        ref = sp.coo_matrix((fx[name + "_vals"], (fx[name + "_rows"], fx[name + "_cols"])), shape=(V, V)).tocsr()
+        ref.sort_indices()
+        assert np.array_equal(G.indptr, ref.indptr) and np.array_equal(G.indices, ref.indices)
+        got = part(G.data).astype(np.float32)
+        assert np.abs(got - ref.data).max() <= 2e-6 * np.abs(ref.data).max()
