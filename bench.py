@@ -333,7 +333,20 @@ def run_aux(args, rank, world, local):
             for p_ in net.parameters():
                 p_.grad = None
             _net_loss(net, x, y, ops_t).backward()
-        ms, launches = timed(step)
+        ms_eager, launches = timed(step)
+        # the same forward + backward as ONE CUDA graph (graphs.GraphedTrainStep): the route the metric is quoted on
+        gts = dn.graphs.GraphedTrainStep(net, _net_loss, (x, y, ops_t))
+
+        def gstep():
+            dn.graphs.GraphedTrainStep.zero_grads(net)
+            gts.replay()
+        ms, _ = timed(gstep)
+        # the graph reproduces the eager gradients
+        step()
+        ref_g = [p_.grad.clone() for p_ in net.parameters()]
+        gstep()
+        torch.cuda.synchronize()
+        graph_vs_eager = max(float((p_.grad - r).abs().max() / (r.abs().max() + 1e-30)) for p_, r in zip(net.parameters(), ref_g))
         with torch.no_grad():
             net.eval()
             ms_f, _ = timed(lambda: _net_loss(net, x, y, ops_t))
@@ -366,7 +379,9 @@ def run_aux(args, rank, world, local):
         line.update({"metric": "DiffusionNet (4 blocks) forward+backward Mverts/sec at V=7056,K=128,C=128",
                      "value": world * V / (ms * 1e-3) / 1e6, "ms_per_step": ms, "scaling": "weak",
                      "config": {"workload": "net_fwd_bwd V=7056 K=128 C=128 4 blocks, 1 mesh per GPU",
-                                "engine": args.engine, "forward_only_ms": ms_f},
+                                "engine": args.engine, "forward_only_ms": ms_f, "route": "forward + backward replayed as one "
+                                "CUDA graph (graphs.GraphedTrainStep)", "eager_autograd_ms": ms_eager,
+                                "graph_vs_eager_max_rel_grad_diff": graph_vs_eager},
                      "gpu_launches": launches, "gpu_baseline": gpu_base})
     elif args.workload == "train":
         # config 5: global batch of 8 meshes (V = 20000 each), data parallel: every rank takes 8 / world meshes, one flat
@@ -380,10 +395,18 @@ def run_aux(args, rank, world, local):
         opt = torch.optim.Adam(net.parameters(), lr=1e-3, fused=True)
         ar_ms = []
 
+        use_graphs = os.environ.get("DN_TRAIN_GRAPHS", "1") != "0"
+        gts = [dn.graphs.GraphedTrainStep(net, _net_loss, m) for m in meshes] if use_graphs else []
+
         def step():
-            opt.zero_grad(set_to_none=True)
-            for x, y, ops_t in meshes:
-                _net_loss(net, x, y, ops_t).backward()         # gradients accumulate over this rank's meshes
+            if use_graphs:                                     # one CUDA graph (forward + backward) per mesh of this rank
+                dn.graphs.GraphedTrainStep.zero_grads(net)
+                for g_ in gts:
+                    g_.replay()
+            else:
+                opt.zero_grad(set_to_none=True)
+                for x, y, ops_t in meshes:
+                    _net_loss(net, x, y, ops_t).backward()     # gradients accumulate over this rank's meshes
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             dn.dist.allreduce_gradients(net.parameters(), n_global_meshes=n_global)
@@ -398,7 +421,8 @@ def run_aux(args, rank, world, local):
         line.update({"metric": "DiffusionNet (4 blocks) data-parallel training step, 8 meshes V=20000, Mverts/sec",
                      "value": Vtot / (ms * 1e-3) / 1e6, "ms_per_step": ms, "scaling": "strong",
                      "config": {"workload": "train 8 meshes V=20000 K=128 C=128 4 blocks, dp{}".format(world),
-                                "engine": args.engine, "meshes_per_rank": len(mine), "optimizer": "Adam",
+                                "engine": args.engine, "meshes_per_rank": len(mine), "optimizer": "Adam (fused)",
+                                "fwd_bwd": "one CUDA graph per mesh (graphs.GraphedTrainStep)" if use_graphs else "eager autograd",
                                 "allreduce": "one flat fp32 buffer of {} floats, NCCL".format(nparam),
                                 "allreduce_ms_median": ar[len(ar) // 2], "allreduce_ms_max": ar[-1]},
                      "gpu_launches": launches})

@@ -575,6 +575,41 @@ def test_net_training_step_and_gradient_allreduce(dn):
     assert float(min(b.diffusion.diffusion_time.min() for b in net.blocks)) >= 0.0
 
 
+def test_graphed_train_step_matches_eager_autograd(dn):
+    """graphs.GraphedTrainStep: forward + backward of a net on one mesh replayed as one CUDA graph accumulates the same
+    gradients as eager autograd (BASELINE configs 2 / 5 are launch-bound in eager mode)."""
+    dn.set_engine("tc3x")
+    net = dn.DiffusionNet(C_in=16, C_out=4, C_width=64, N_block=2, dropout=False).cuda().train()
+    with torch.no_grad():
+        for n_, p_ in net.named_parameters():
+            if n_.endswith("diffusion_time"):
+                p_.uniform_(1e-3, 0.3)
+    mass, L, evals, evecs, gX, gY = dn.synthetic.structural_operators(20, 24, 64, seed=1, device="cuda")
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(480, 16, generator=g).cuda()
+    y = torch.randint(0, 4, (480,), generator=g).cuda()
+
+    def loss_fn(net_, x_, y_):
+        return torch.nn.functional.cross_entropy(net_(x_, mass, evals=evals, evecs=evecs, gradX=gX, gradY=gY), y_)
+
+    for p_ in net.parameters():
+        p_.grad = None
+    loss_fn(net, x, y).backward()
+    ref = [p_.grad.clone() for p_ in net.parameters()]
+    gts = dn.graphs.GraphedTrainStep(net, loss_fn, (x, y))
+    for rep in range(2):
+        dn.graphs.GraphedTrainStep.zero_grads(net)
+        loss = gts.replay()
+        torch.cuda.synchronize()
+        assert torch.isfinite(loss)
+        for p_, r in zip(net.parameters(), ref):
+            assert torch.equal(p_.grad, r)
+    gts.replay()                                            # a second replay without zeroing accumulates: 2 x the gradient
+    torch.cuda.synchronize()
+    for p_, r in zip(net.parameters(), ref):
+        assert torch.allclose(p_.grad, 2 * r, rtol=1e-6, atol=0)
+
+
 # ---- data-side neighbours of the block (SURVEY.md 8f items 2-3) ------------------------------------------------
 GEOM_CACHE = os.path.join(ROOT, "tests", "golden", "op_cache")
 
