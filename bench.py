@@ -690,6 +690,9 @@ def main():
         lins = blk.mlp.linears()
         nprof = 10
         acc = [0.0] * len(dn.ops.PROFILE_STAGES)
+        import ctypes
+        lib.dn_debug_gf_gather_ms.restype = ctypes.c_float
+        gather_acc = 0.0
         with torch.no_grad():
             for it in range(nprof + 2):
                 prof = []
@@ -697,7 +700,9 @@ def main():
                                          [l.weight for l in lins], [l.bias for l in lins], True, profile=prof)
                 if it >= 2:
                     acc = [a + b for a, b in zip(acc, prof)]
+                    gather_acc += float(lib.dn_debug_gf_gather_ms())     # the x-only gather's share of stage [4] (0: old route)
         stages = {n + "_ms": a / nprof for n, a in zip(dn.ops.PROFILE_STAGES, acc)}
+        gather_x_ms = gather_acc / nprof
 
     # ---- the reference beside it (rank 0, N=1 only; bounded samples) ----
     cpu, gpu_base = None, None
@@ -764,9 +769,26 @@ def main():
                 traffic = json.load(fh)
         except Exception:
             traffic = {}
+        tc_route = gather_x_ms > 0.0      # tensor-core gradient features (default at C = 128): stage [4] is three launches
+        if not tc_route:                  # commuted route (DN_GF_TC=0): [P|Q] fused behind from_basis, one gather kernel
+            work["from_basis_pq"] = (4 * V * (K + C + 2 * C), (2 * K * C + 4 * C * C) * V,
+                                     "rows_chain3_kernel (from_basis -> [P|Q], 2 fused layers)")
+            work["grad_features_gather"] = (4 * V * (3 * C + C) + 12 * nnz + 4 * V, 12 * NNZ_ROW * C * V,
+                                            "spmm_features_blk_kernel (CSR gather of x, P, Q + inner product + tanh)")
         kernels = []
-        for name in dn.ops.PROFILE_STAGES:
-            ms = stages[name + "_ms"]
+        names = list(dn.ops.PROFILE_STAGES)
+        times = {n: stages[n + "_ms"] for n in names}
+        if tc_route:
+            i = names.index("grad_features_gather")
+            names[i:i + 1] = ["grad_gather_x", "grad_dots_gemm"]
+            times["grad_gather_x"] = gather_x_ms
+            times["grad_dots_gemm"] = (stages["grad_features_gather_ms"] - gather_x_ms) / 2      # per launch (two launches)
+            work["grad_gather_x"] = (4 * V * (C + 2 * C) + 12 * nnz + 4 * V, 4 * NNZ_ROW * C * V,
+                                     "spmm_gxy_blk_kernel (x-only CSR gather, writes [gX|gY])")
+            work["grad_dots_gemm"] = (4 * V * (2 * C + C + C // 2), 4 * C * C * V,
+                                      "rows_chain3_kernel ([gX|gY] W_rot for 64 channels, tanh(gX*Bre+gY*Bim) epilogue; one of 2 launches)")
+        for name in names:
+            ms = times[name]
             by, fl, kname = work[name]
             ms = max(ms, 1e-6)
             gbs = by / (ms * 1e-3) / 1e9
