@@ -445,70 +445,97 @@ __device__ __forceinline__ void fma2(unsigned long long& d, unsigned long long a
 constexpr int GB_ROWS = 64;      // rows per CTA
 constexpr int GB_NNZ = 1024;     // staged entries per CTA (entries past it are read from global memory)
 
-template <bool ROT, int NB, int MINB, int NH>
-__global__ void __launch_bounds__(256, MINB)
+struct __align__(16) GxyEnt { int col; int pad; float gx, gy; };   // (gx, gy) 8-byte aligned: one LDS.64
+
+// one CSR entry of the (x, P, Q) gather: three 16-byte slices of the neighbour's rows, then 12 FFMA2
+#define DN_FEAT_LOAD(J, ENT)                                                                         \
+  const char* pr##J;                                                                                 \
+  ulonglong2 x##J, P##J, Q##J = make_ulonglong2(0ull, 0ull);                                         \
+  {                                                                                                  \
+    const int64_t col = (ENT).col;                                                                   \
+    x##J = __ldg(reinterpret_cast<const ulonglong2*>(xb + col * x_row_bytes));                       \
+    pr##J = pb + col * pq_row_bytes;                                                                 \
+    P##J = __ldg(reinterpret_cast<const ulonglong2*>(pr##J));                                        \
+    if (ROT) Q##J = __ldg(reinterpret_cast<const ulonglong2*>(pr##J + x_row_bytes));                 \
+  }
+// (the weights are re-read from the staged entry at FMA time: a broadcast LDS.64 is cheaper than 14 live registers)
+#define DN_FEAT_FMA(J, ENT)                                                                          \
+  {                                                                                                  \
+    const float2 w = *reinterpret_cast<const float2*>(&(ENT).gx);                                    \
+    const unsigned long long gx2 = pack2(w.x, w.x), gy2 = pack2(w.y, w.y);                           \
+    fma2(gX0, gx2, x##J.x); fma2(gX1, gx2, x##J.y);                                                  \
+    fma2(gY0, gy2, x##J.x); fma2(gY1, gy2, x##J.y);                                                  \
+    fma2(re0, gx2, P##J.x); fma2(re1, gx2, P##J.y);                                                  \
+    fma2(im0, gy2, P##J.x); fma2(im1, gy2, P##J.y);                                                  \
+    if (ROT) {                                                                                       \
+      const unsigned long long ngy2 = pack2(-w.y, -w.y);                                             \
+      fma2(re0, ngy2, Q##J.x); fma2(re1, ngy2, Q##J.y);                                              \
+      fma2(im0, gx2, Q##J.x); fma2(im1, gx2, Q##J.y);                                                \
+    }                                                                                                \
+  }
+
+// (Same staging as spmm_gxy_blk_kernel below: 16-byte entry records, unpredicated full batches -- the first version,
+// with per-entry predicates and separate col / value arrays, spent half of its issue slots on bookkeeping.)
+template <bool ROT, int NH>
+__global__ void __launch_bounds__(256, 2)
 spmm_features_blk_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                          const float2* __restrict__ vals, const float* __restrict__ xd,
                          const float* __restrict__ pq, int ld_pq, int64_t V, float* __restrict__ feat) {
   constexpr int C = 128 * NH;          // a warp covers 128 channels per pass (one float4 per lane), NH passes per row
+  constexpr int64_t x_row_bytes = (int64_t)C * 4;
   __shared__ int s_rp[GB_ROWS + 1];
-  __shared__ int s_col[GB_NNZ];
-  __shared__ float2 s_g[GB_NNZ];
+  __shared__ GxyEnt s_e[GB_NNZ];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t base = (int64_t)blockIdx.x * GB_ROWS;
   const int nrows = (int)((V - base) < GB_ROWS ? (V - base) : GB_ROWS);
   if ((int)threadIdx.x <= nrows) s_rp[threadIdx.x] = __ldg(rowptr + base + threadIdx.x);
   __syncthreads();
   const int e0 = s_rp[0];
-  {
-    const int tot = s_rp[nrows] - e0;
-    const int cnt = tot < GB_NNZ ? tot : GB_NNZ;
-    for (int i = threadIdx.x; i < cnt; i += 256) {
-      s_col[i] = __ldg(colidx + e0 + i);
-      s_g[i] = __ldg(vals + e0 + i);
+  const int tot = s_rp[nrows] - e0;
+  const bool staged = tot <= GB_NNZ;                              // (block-uniform)
+  if (staged) {
+    for (int i = threadIdx.x; i < tot; i += 256) {
+      const float2 g = __ldg(vals + e0 + i);
+      GxyEnt en;
+      en.col = __ldg(colidx + e0 + i); en.gx = g.x; en.gy = g.y; en.pad = 0;
+      s_e[i] = en;
     }
   }
   __syncthreads();
-  constexpr int64_t x_row_bytes = (int64_t)C * 4;
   const int64_t pq_row_bytes = (int64_t)ld_pq * 4;
+#pragma unroll 1
   for (int rh = warp; rh < nrows * NH; rh += 8) {
     const int r = rh / NH, h = rh % NH;
     const char* xb = reinterpret_cast<const char*>(xd) + h * 512 + lane * 16;
     const char* pb = reinterpret_cast<const char*>(pq) + h * 512 + lane * 16;
     const int s = s_rp[r] - e0, e = s_rp[r + 1] - e0;
     unsigned long long gX0 = 0ull, gX1 = 0ull, gY0 = 0ull, gY1 = 0ull, re0 = 0ull, re1 = 0ull, im0 = 0ull, im1 = 0ull;
-    for (int p0 = s; p0 < e; p0 += NB) {
-      ulonglong2 x[NB], P[NB], Q[NB];
-      float wx[NB], wy[NB];
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const int p = p0 + j;
-        if (p < e) {                                             // (warp-uniform)
-          int col;
-          float2 g;
-          if (p < GB_NNZ) { col = s_col[p]; g = s_g[p]; }
-          else { col = __ldg(colidx + e0 + p); g = __ldg(vals + e0 + p); }
-          wx[j] = g.x; wy[j] = g.y;
-          x[j] = __ldg(reinterpret_cast<const ulonglong2*>(xb + (int64_t)col * x_row_bytes));
-          const char* pr = pb + (int64_t)col * pq_row_bytes;
-          P[j] = __ldg(reinterpret_cast<const ulonglong2*>(pr));
-          if (ROT) Q[j] = __ldg(reinterpret_cast<const ulonglong2*>(pr + x_row_bytes));
-        }
+    if (staged) {
+      int p = s;
+#pragma unroll 1
+      for (; p + 7 <= e; p += 7) {                                // full batches: 21 independent loads, no predicates
+        DN_FEAT_LOAD(0, s_e[p]) DN_FEAT_LOAD(1, s_e[p + 1]) DN_FEAT_LOAD(2, s_e[p + 2]) DN_FEAT_LOAD(3, s_e[p + 3])
+        DN_FEAT_LOAD(4, s_e[p + 4]) DN_FEAT_LOAD(5, s_e[p + 5]) DN_FEAT_LOAD(6, s_e[p + 6])
+        DN_FEAT_FMA(0, s_e[p]) DN_FEAT_FMA(1, s_e[p + 1]) DN_FEAT_FMA(2, s_e[p + 2]) DN_FEAT_FMA(3, s_e[p + 3])
+        DN_FEAT_FMA(4, s_e[p + 4]) DN_FEAT_FMA(5, s_e[p + 5]) DN_FEAT_FMA(6, s_e[p + 6])
       }
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        if (p0 + j < e) {
-          const unsigned long long gx2 = pack2(wx[j], wx[j]), gy2 = pack2(wy[j], wy[j]);
-          fma2(gX0, gx2, x[j].x); fma2(gX1, gx2, x[j].y);
-          fma2(gY0, gy2, x[j].x); fma2(gY1, gy2, x[j].y);
-          fma2(re0, gx2, P[j].x); fma2(re1, gx2, P[j].y);
-          fma2(im0, gy2, P[j].x); fma2(im1, gy2, P[j].y);
-          if (ROT) {
-            const unsigned long long ngy2 = pack2(-wy[j], -wy[j]);
-            fma2(re0, ngy2, Q[j].x); fma2(re1, ngy2, Q[j].y);
-            fma2(im0, gx2, Q[j].x); fma2(im1, gx2, Q[j].y);
-          }
-        }
+#pragma unroll 1
+      for (; p + 2 <= e; p += 2) {                                // remainder: pairs, then a single entry
+        DN_FEAT_LOAD(0, s_e[p]) DN_FEAT_LOAD(1, s_e[p + 1])
+        DN_FEAT_FMA(0, s_e[p]) DN_FEAT_FMA(1, s_e[p + 1])
+      }
+      if (p < e) {
+        DN_FEAT_LOAD(0, s_e[p])
+        DN_FEAT_FMA(0, s_e[p])
+      }
+    } else {
+#pragma unroll 1
+      for (int p = s; p < e; ++p) {                               // (a block with more than GB_NNZ entries)
+        GxyEnt en;
+        const float2 g = __ldg(vals + e0 + p);
+        en.col = __ldg(colidx + e0 + p); en.gx = g.x; en.gy = g.y; en.pad = 0;
+        DN_FEAT_LOAD(0, en)
+        DN_FEAT_FMA(0, en)
       }
     }
     float gXv[4], gYv[4], rev[4], imv[4];
@@ -524,13 +551,15 @@ spmm_features_blk_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
     *reinterpret_cast<float4*>(feat + (base + r) * C + h * 128 + lane * 4) = o;
   }
 }
+#undef DN_FEAT_LOAD
+#undef DN_FEAT_FMA
 
 // The same block gather for the tensor-core gradient-features route: only x_diffuse is gathered (7 x 512 B per
 // vertex instead of 7 x 1.5 KB) and the raw tangent gradients are written out,
 //     gxy[v] = [ sum_j gx_vj x_j | sum_j gy_vj x_j ]                                       (layers.py:216-223)
 // the complex-linear map, the inner product and the tanh follow as a tcgen05 GEMM with a fused epilogue (rows_chain3,
 // has_res == 3).  Entry order = CSR order, fmaf per element (as FFMA2).
-struct __align__(16) GxyEnt { int col; float gx, gy; int pad; };
+
 
 // One CSR entry of the x-only gather: the neighbour row's 16-byte slice is loaded, then 4 FFMA2 -- gX += gx * x, gY += gy * x
 #define DN_GXY_LOAD(J, ENT)                                                                          \
@@ -538,7 +567,7 @@ struct __align__(16) GxyEnt { int col; float gx, gy; int pad; };
   const ulonglong2 x##J = __ldg(reinterpret_cast<const ulonglong2*>(xb + (int64_t)en##J.x * x_row_bytes));
 #define DN_GXY_FMA(J)                                                                                \
   {                                                                                                  \
-    const float wx = __int_as_float(en##J.y), wy = __int_as_float(en##J.z);                          \
+    const float wx = __int_as_float(en##J.z), wy = __int_as_float(en##J.w);                          \
     const unsigned long long gx2 = pack2(wx, wx), gy2 = pack2(wy, wy);                               \
     fma2(gX0, gx2, x##J.x); fma2(gX1, gx2, x##J.y);                                                  \
     fma2(gY0, gy2, x##J.x); fma2(gY1, gy2, x##J.y);                                                  \
@@ -970,7 +999,7 @@ int launch_spmm_features(const dn_csr* g, const float* xd, const float* pq, int 
     const unsigned ctas = (unsigned)((V + GB_ROWS - 1) / GB_ROWS);
     const int ld = rotations ? 2 * C : C;
 #define DN_BLK_LAUNCH(ROT_, NH_) \
-    spmm_features_blk_kernel<ROT_, 7, 2, NH_><<<ctas, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, feat)
+    spmm_features_blk_kernel<ROT_, NH_><<<ctas, 256, 0, st>>>(g->rowptr, g->colidx, vals, xd, pq, ld, V, feat)
     if (rotations) { if (C == 128) DN_BLK_LAUNCH(true, 1); else DN_BLK_LAUNCH(true, 2); }
     else { if (C == 128) DN_BLK_LAUNCH(false, 1); else DN_BLK_LAUNCH(false, 2); }
 #undef DN_BLK_LAUNCH
