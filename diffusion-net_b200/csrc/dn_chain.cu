@@ -77,6 +77,7 @@ struct C3Params {
   int ns_shift;    // log2(ring depth): 2 -> 4 stages (32 KiB weight slots), 1 -> 2 stages (64 KiB weight slots)
   int nr_shift;    // log2(row-box slots): 2 or 1;  output staging buffers = nio - slots
   int nio;         // 16 KiB row-box + staging buffers in front of the weight ring: 6 (weight ring 128 KiB) or 8 (96 KiB)
+  int pair;        // 1: the MMA warp takes ring stages in pairs (4-slot rings only)
   int64_t V;
   long long* trace;   // optional (tools/trace_chain3.py): per-warp (event, clock64) pairs of CTA 0
   const int32_t* tile_group;   // optional (mesh batches): layer 0 of tile t streams the packed matrix number tile_group[t]
@@ -269,45 +270,54 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         }
         tc_fence_after();
         C3_TRACE(24);
-        for (int c = 0; c < nst; ++c, ++i) {
-          const uint32_t s = i & ns_mask, ph = (i >> ns_sh) & 1u;
+        // Stages are handed over in PAIRS when the ring has four slots: the fixed cost of a hand-off in this warp (barrier
+        // poll, fence, elect, descriptor setup, commits: ~450 cycles during which the tensor pipe drains -- the MMA queue
+        // is shallow, `tcgen05.mma` issue blocks for about the execution time) is then paid once per 16 MMAs instead of
+        // once per 8, while the operand warps fill the other two slots.  (A 128x128x8 MMA retires in 64 cycles when MMAs
+        // are issued back to back, tools/ubench/ubench3.cu: 8 per stage = 512 cycles against ~1100 measured per stage.)
+        const int step = (p.pair && ns_sh == 2) ? 2 : 1;
+        for (int c = 0; c < nst; c += step, i += (uint32_t)step) {
           C3_TRACE(20);
-          mbar_wait(full + 8 * s, ph);
+          for (int h = 0; h < step; ++h) mbar_wait(full + 8 * ((i + (uint32_t)h) & ns_mask), ((i + (uint32_t)h) >> ns_sh) & 1u);
           C3_TRACE(21);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t a0 = tmem_base + (uint32_t)p.ring_col + s * 64u;
-            const uint64_t dbs = tmplB + (w_u4 + s * (w_slot >> 4));
-            if (p.passes == 2) {
-              // stage = [tf32 hi image | bf16 (hi ; lo) image], k-group stride N * 16 B in both.  Four TF32 MMAs (K = 8)
-              // form hi*hi; four bf16 MMAs (K = 16) add the corrections [x_lo | x_hi] . [W_hi ; W_lo] -- 8 instructions and
-              // 32 KiB of shared-memory operand reads per stage where 3xTF32 needs 12 and 48 KiB, same fp32-grade result
-              const uint32_t kg2 = (2u * b_lbo) >> 4;
+            for (int h = 0; h < step; ++h) {
+              const uint32_t s = (i + (uint32_t)h) & ns_mask;
+              const int cc = c + h;
+              const uint32_t a0 = tmem_base + (uint32_t)p.ring_col + s * 64u;
+              const uint64_t dbs = tmplB + (w_u4 + s * (w_slot >> 4));
+              if (p.passes == 2) {
+                // stage = [tf32 hi image | bf16 (hi ; lo) image], k-group stride N * 16 B in both.  Four TF32 MMAs (K = 8)
+                // form hi*hi; four bf16 MMAs (K = 16) add the corrections [x_lo | x_hi] . [W_hi ; W_lo] -- 8 instructions
+                // and 32 KiB of shared-memory operand reads per stage where 3xTF32 needs 12 and 48 KiB, same fp32-grade result
+                const uint32_t kg2 = (2u * b_lbo) >> 4;
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                mma_tf32_ts(d_tmem, a0 + ks * 8, dbs + (uint32_t)ks * kg2, idesc, (c | ks) ? 1u : 0u);
-              const uint64_t db16 = dbs + (((uint32_t)N * 128u) >> 4);
+                for (int ks = 0; ks < 4; ++ks)
+                  mma_tf32_ts(d_tmem, a0 + ks * 8, dbs + (uint32_t)ks * kg2, idesc, (cc | ks) ? 1u : 0u);
+                const uint64_t db16 = dbs + (((uint32_t)N * 128u) >> 4);
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                mma_f16_ts(d_tmem, a0 + 32 + j * 8, db16 + (uint32_t)j * kg2, idesc16, 1u);
-            } else {
+                for (int j = 0; j < 4; ++j)
+                  mma_f16_ts(d_tmem, a0 + 32 + j * 8, db16 + (uint32_t)j * kg2, idesc16, 1u);
+              } else {
 #pragma unroll
-              for (int ks = 0; ks < C3_KS / 8; ++ks) {
-                const uint32_t a_hi = a0 + ks * 8, a_lo = a_hi + 32;
-                const uint64_t b_h = p.fmt ? dbs + (uint32_t)ks * b_ks_u
-                                           : dbs + (uint32_t)(ks >> 1) * b_chunk_u + (uint32_t)(ks & 1) * b_ks_u;
-                const uint32_t acc = (c | ks) ? 1u : 0u;
-                if (p.passes == 3) {
-                  mma_tf32_ts(d_tmem, a_lo, b_h, idesc, acc);
-                  mma_tf32_ts(d_tmem, a_hi, b_h + b_img_u, idesc, 1u);
-                  mma_tf32_ts(d_tmem, a_hi, b_h, idesc, 1u);
-                } else {
-                  mma_tf32_ts(d_tmem, a_hi, b_h, idesc, acc);
+                for (int ks = 0; ks < C3_KS / 8; ++ks) {
+                  const uint32_t a_hi = a0 + ks * 8, a_lo = a_hi + 32;
+                  const uint64_t b_h = p.fmt ? dbs + (uint32_t)ks * b_ks_u
+                                             : dbs + (uint32_t)(ks >> 1) * b_chunk_u + (uint32_t)(ks & 1) * b_ks_u;
+                  const uint32_t acc = (cc | ks) ? 1u : 0u;
+                  if (p.passes == 3) {
+                    mma_tf32_ts(d_tmem, a_lo, b_h, idesc, acc);
+                    mma_tf32_ts(d_tmem, a_hi, b_h + b_img_u, idesc, 1u);
+                    mma_tf32_ts(d_tmem, a_hi, b_h, idesc, 1u);
+                  } else {
+                    mma_tf32_ts(d_tmem, a_hi, b_h, idesc, acc);
+                  }
                 }
               }
+              mma_commit(ab_empty + 8 * s);           // frees TMEM operand stage s and weight stage s
             }
-            mma_commit(ab_empty + 8 * s);             // frees TMEM operand stage s and weight stage s
-            if (c + 1 == nst) {
+            if (c + step == nst) {
               if (l + 1 < L) mma_commit(dm_full + 8 * buf);
               if (p.layer[l].has_out) mma_commit(do_full + 8 * buf);
             }
@@ -793,6 +803,11 @@ int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, in
   //  with the tensor core for shared-memory bandwidth -- so 4 + 2 stays the default; DN_C3_NR=2 selects 2 + 4)
   p.nr_shift = 2;
   p.nio = C3_IO_BUFS;
+  {
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("DN_C3_PAIR"); pair_env = e ? atoi(e) : 1; }
+    p.pair = pair_env;
+  }
   if (n_layers == 1 && layers[0].dots_src && nmax <= 128) {
     // complex-dots layer: 4 row boxes + 4 staging buffers (all gX / gY boxes of a tile prefetched) + a 2-stage ring
     p.nio = 8; p.ns_shift = 1;
