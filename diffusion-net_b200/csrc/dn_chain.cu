@@ -416,13 +416,6 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         const uint32_t g = t_seq * (uint32_t)L + (uint32_t)l;
         const uint32_t buf = two ? (g & 1u) : 0u;
         const int nco = Lr.N / C3_KS;
-        // this warpgroup's chunks are c = wg, wg + 2, ... (at most 4 at N = 256): their bias lanes, in flight during the wait
-        float bl[4] = {0.f, 0.f, 0.f, 0.f};
-        if (Lr.bias) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if ((int)wg + 2 * q < nco) bl[q] = __ldg(Lr.bias + ((int)wg + 2 * q) * C3_KS + lane);
-        }
         C3_TRACE(10);
         mbar_wait(dm_full + 8 * buf, (buf ? um1 : um0) & 1u);
         C3_TRACE(11);
@@ -432,6 +425,13 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         bool released = false;
         for (int c = (int)wg; c < nco; c += 2) {
           float v[32];
+          // the chunk's 32 bias values: eight uniform-address (broadcast) 16-byte loads, in flight during the TMEM read
+          // (a 32-step shuffle broadcast of per-lane values cost ~450 cycles on the critical path of every layer boundary)
+          float4 b4[8];
+          if (Lr.bias) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) b4[jj] = __ldg(reinterpret_cast<const float4*>(Lr.bias + c * C3_KS) + jj);
+          }
           tmem_ld32(d_lane + (uint32_t)c * C3_KS, v);
           C3_TRACE(12);
           if (c + 2 >= nco) {                                    // my last read of this accumulator
@@ -441,10 +441,10 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
             released = true;
           }
           if (Lr.bias) {
-            const int qi = (c - (int)wg) >> 1;
-            const float mine = qi == 0 ? bl[0] : (qi == 1 ? bl[1] : (qi == 2 ? bl[2] : bl[3]));
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, mine, j);
+            for (int jj = 0; jj < 8; ++jj) {
+              v[4 * jj] += b4[jj].x; v[4 * jj + 1] += b4[jj].y; v[4 * jj + 2] += b4[jj].z; v[4 * jj + 3] += b4[jj].w;
+            }
           }
           if (Lr.relu) {
 #pragma unroll
@@ -549,12 +549,6 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         }
         const bool res = Lr.has_res != 0;
         const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
-        float bl[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // bias lane of each chunk (N <= 256)
-        if (Lr.bias) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (q < nco) bl[q] = __ldg(Lr.bias + q * C3_KS + lane);
-        }
         C3_TRACE(30);
         if (!res) {
           mbar_wait(do_full + 8 * buf, use & 1u);
@@ -593,6 +587,11 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
             }
             C3_TRACE(32);
             float v[32];
+            float4 b4[8];                                        // bias of the chunk: broadcast loads under the TMEM read
+            if (Lr.bias) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) b4[jj] = __ldg(reinterpret_cast<const float4*>(Lr.bias + c * C3_KS) + jj);
+            }
             tmem_ld32(d_lane + (uint32_t)c * C3_KS, v);
             C3_TRACE(33);
             if (c + 1 == nco) {                                  // last read of this accumulator by this warp
@@ -601,11 +600,10 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
               if (lane == 0) mbar_arrive(do_empty + 8 * buf);
             }
             if (Lr.bias) {
-              float mine = bl[0];
 #pragma unroll
-              for (int q = 1; q < 8; ++q) mine = (c == q) ? bl[q] : mine;
-#pragma unroll
-              for (int jj = 0; jj < 32; ++jj) v[jj] += __shfl_sync(0xffffffffu, mine, jj);
+              for (int jj = 0; jj < 8; ++jj) {
+                v[4 * jj] += b4[jj].x; v[4 * jj + 1] += b4[jj].y; v[4 * jj + 2] += b4[jj].z; v[4 * jj + 3] += b4[jj].w;
+              }
             }
             if (Lr.relu) {
 #pragma unroll
