@@ -785,7 +785,8 @@ def main():
             times["grad_dots_gemm"] = (stages["grad_features_gather_ms"] - gather_x_ms) / 2      # per launch (two launches)
             work["grad_gather_x"] = (4 * V * (C + 2 * C) + 12 * nnz + 4 * V, 4 * NNZ_ROW * C * V,
                                      "spmm_gxy_blk_kernel (x-only CSR gather, writes [gX|gY])")
-            work["grad_dots_gemm"] = (4 * V * (2 * C + C + C // 2), 4 * C * C * V,
+            # (the epilogue's second read of the 64 gX / gY columns it needs comes out of L2: not counted)
+            work["grad_dots_gemm"] = (4 * V * (2 * C + C // 2), 4 * C * C * V,
                                       "rows_chain3_kernel ([gX|gY] W_rot for 64 channels, tanh(gX*Bre+gY*Bim) epilogue; one of 2 launches)")
         for name in names:
             ms = times[name]
