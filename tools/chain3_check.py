@@ -2,8 +2,8 @@
 for the two fused chains of the block (from_basis + [P|Q]; MiniMLP + skip) and single layers, at several V
 (ragged last tile, V < 128, one tile, many tiles per CTA), repeated calls to catch hand-off races.
 
-    python tools/r2_chain3_check.py            # default path (DN_TC_CHAIN3=1)
-    DN_TC_CHAIN3=0 python tools/r2_chain3_check.py   # the round-1 kernels, for the A/B
+    python tools/chain3_check.py            # default path (DN_TC_CHAIN3=1)
+    DN_TC_CHAIN3=0 python tools/chain3_check.py   # the round-1 kernels, for the A/B
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

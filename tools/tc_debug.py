@@ -1,14 +1,11 @@
 """Bring-up probe for the tcgen05 engine: small GEMMs through the C-ABI vs fp64 torch, with
 one-hot probes that print the operand-layout mapping when a result is wrong.
-Usage: python tools/tc_debug.py [variant]   (variant sets DN_TC_VARIANT for the library)"""
+Usage: python tools/tc_debug.py"""
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-if len(sys.argv) > 1:
-    os.environ["DN_TC_VARIANT"] = sys.argv[1]
-
 import torch  # noqa: E402
 import diffusion_net_b200 as dn  # noqa: E402
 
@@ -57,7 +54,7 @@ def onehot_probe():
 
 
 if __name__ == "__main__":
-    print("variant", os.environ.get("DN_TC_VARIANT", "0"), "device", torch.cuda.get_device_name(0), flush=True)
+    print("device", torch.cuda.get_device_name(0), flush=True)
     for eng in ("simt", "tc1x", "tc3x"):
         for (V, K, C) in [(128, 32, 16), (128, 128, 128), (1000, 128, 128), (4096, 64, 256)]:
             e, out, ref = from_basis_case(V, K, C, eng)
