@@ -68,6 +68,10 @@ class dn_mesh_batch(C.Structure):
                 ("mesh_cta_begin", C.c_void_p)]
 
 
+class dn_head(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("n_out", C.c_int32), ("out", C.c_void_p), ("ld_out", C.c_int64)]
+
+
 _P, _I, _L = C.c_void_p, C.c_int, C.c_int64
 _PP = C.POINTER(C.c_void_p)
 _IP = C.POINTER(C.c_int)
@@ -100,6 +104,8 @@ SIGNATURES = {
                                   _I, _P, C.POINTER(C.c_float)]),
     "dn_build_grad": (_I, [_P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _L, _P]),
     "dn_mesh_batch_plan": (_I, [_I, _P, _I, _P, _P, _P, _P]),
+    "dn_block_fwd_ex": (_I, [_P, _P, _P, _P, C.POINTER(dn_csr), C.POINTER(dn_block_params), C.POINTER(dn_mesh_batch),
+                             C.POINTER(dn_head), _L, _I, _I, _P, _P, _L, _I, _P]),
     "dn_block_fwd_batched": (_I, [_P, _P, _P, _P, C.POINTER(dn_csr), C.POINTER(dn_block_params), C.POINTER(dn_mesh_batch),
                                   _L, _I, _I, _P, _P, _L, _I, _P]),
 }
@@ -122,7 +128,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.dn_abi_version() != 4:
+    if lib.dn_abi_version() != 5:
         raise RuntimeError("diffusion_net_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -98,29 +98,11 @@ class MeshBatch:
         return [y[self.row_begin[b]:self.row_begin[b] + self.n_rows[b]] for b in range(self.n_meshes)]
 
 
-def block_forward_batched_raw(batch, x_in, time, A_re, A_im, weights, biases, with_features):
-    """dn_block_fwd_batched: one DiffusionNetBlock (eval) over every mesh of ``batch`` (x_in in the batch layout)."""
-    lib = _lib.load()
+def block_forward_batched_raw(batch, x_in, time, A_re, A_im, weights, biases, with_features, head=None):
+    """dn_block_fwd_ex with a batch descriptor: one DiffusionNetBlock (eval) over every mesh of ``batch`` (x_in in the batch
+    layout).  ``head``: see ops.block_forward_raw."""
     x_in = ops._f32c(x_in)
-    V, Cc = x_in.shape
-    if V != batch.V:
-        raise ValueError("x_in is not in this batch's layout ({} rows, expected {})".format(V, batch.V))
-    out = torch.empty_like(x_in)
-    dims = [weights[0].shape[1]] + [w.shape[0] for w in weights]
-    wc = [ops._f32c(w) for w in weights]
-    bc = [ops._f32c(b) if b is not None else None for b in biases]
-    a_re = ops._f32c(A_re) if A_re is not None else None
-    a_im = ops._f32c(A_im) if A_im is not None else None
-    wp = _lib.ptr_array([w.data_ptr() for w in wc])
-    bp = _lib.ptr_array([b.data_ptr() if b is not None else None for b in bc])
-    dm = _lib.int_array(dims)
-    prm = _lib.dn_block_params(time.data_ptr(), a_re.data_ptr() if a_re is not None else None,
-                               a_im.data_ptr() if a_im is not None else None, 1 if with_features else 0,
-                               1 if a_im is not None else 0, len(weights), wp, bp, dm)
-    with ops._on(x_in):
-        ws = ops.workspace(V, batch.K, max(Cc, max(dims[1:])), x_in.device, extra=batch.n_meshes * batch.K * Cc * 8)
-        _lib.check(lib.dn_block_fwd_batched(x_in.data_ptr(), batch.mass.data_ptr(), batch.evals.data_ptr(),
-                                            batch.evecs.data_ptr(), C.byref(batch.gops.csr[0]), C.byref(prm),
-                                            C.byref(batch.desc), V, batch.K, Cc, out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                            ops._engine, ops._stream()), "dn_block_fwd_batched")
-    return out
+    if x_in.shape[0] != batch.V:
+        raise ValueError("x_in is not in this batch's layout ({} rows, expected {})".format(x_in.shape[0], batch.V))
+    return ops.block_forward_raw(x_in, batch.mass, batch.evals, batch.evecs, batch.gops, time, A_re, A_im, weights, biases,
+                                 with_features, head=head, batch_desc=batch.desc)

@@ -599,10 +599,12 @@ int dn_mini_mlp_bwd(const float* grad_out, const float* const* src_host, const i
 static int block_fwd_impl(const float* x_in, const float* mass, const float* evals, const float* evecs,
                           const dn_csr* grad, const dn_block_params* p, int64_t V, int K, int C, float* out,
                           void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream, cudaEvent_t* ev,
-                          const dn_mesh_batch* batch = nullptr) {
+                          const dn_mesh_batch* batch = nullptr, const dn_head* head = nullptr) {
   // ev (optional, DN_PROFILE_STAGES + 1 events): recorded on the launching stream between the stages
   auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], (cudaStream_t)stream); };
-  if (!x_in || !mass || !evals || !evecs || !p || !p->diffusion_time || !out || V < 0 || K <= 0 || C <= 0)
+  if (!x_in || !mass || !evals || !evecs || !p || !p->diffusion_time || (!out && !head) || V < 0 || K <= 0 || C <= 0)
+    return DN_ERR_INVALID_ARGUMENT;
+  if (head && (!head->weight || !head->out || head->n_out < 1 || head->n_out > 8 || head->ld_out < head->n_out))
     return DN_ERR_INVALID_ARGUMENT;
   if (p->with_gradient_features && (!grad || !grad->rowptr || !p->A_re || (p->with_gradient_rotations && !p->A_im)))
     return DN_ERR_INVALID_ARGUMENT;
@@ -692,7 +694,15 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
     L[nfront + l] = make_layer(p->mlp_weight_host[l], p->mlp_dims_host[l], 0,
                                p->mlp_bias_host ? p->mlp_bias_host[l] : nullptr, last ? 0 : 1, p->mlp_dims_host[l],
                                p->mlp_dims_host[l + 1], last ? out : nullptr, p->mlp_dims_host[l + 1]);
-    if (last) { L[nfront + l].residual = x_in; L[nfront + l].ld_res = C; }
+    if (last) {
+      L[nfront + l].residual = x_in; L[nfront + l].ld_res = C;
+      if (head) {        // DiffusionNet.last_lin in this layer's epilogue; the block output itself is not stored
+        DnLayer& Lh = L[nfront + l];
+        Lh.head_w = head->weight; Lh.head_b = head->bias; Lh.head_out = head->out; Lh.ld_head_out = head->ld_out;
+        Lh.head_n = head->n_out;
+        if (!out) Lh.out = nullptr;
+      }
+    }
     if (p->mlp_dims_host[l + 1] > maxn) maxn = p->mlp_dims_host[l + 1];
   }
   if (p->mlp_dims_host[nm] != C) return DN_ERR_INVALID_ARGUMENT;
@@ -715,6 +725,7 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
   }
   if (gf_tc && !tc_front) return DN_ERR_UNSUPPORTED;         // (from_basis outside the envelope: cannot happen at C = 128)
   const bool tc_mlp = tc && tc_rows_chain_supported(src_mlp, &L[nfront], nm, passes) == DN_OK;
+  if (head && !tc_mlp) return DN_ERR_UNSUPPORTED;
   // the spectral multiplier S = exp(-lambda t) * (reduced partial sums) is layer 0's weight: when the tensor-core path
   // takes the front chain it is formed inside the pack launch (no separate scale kernel, S never round-trips HBM)
   if (batch && !tc_front) return DN_ERR_UNSUPPORTED;
@@ -804,6 +815,12 @@ int dn_block_fwd_batched(const float* x_in, const float* mass, const float* eval
                          void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream) {
   if (!batch) return DN_ERR_INVALID_ARGUMENT;
   return block_fwd_impl(x_in, mass, evals, evecs, grad, p, V, K, C, out, workspace, ws_bytes, engine, stream, nullptr, batch);
+}
+
+int dn_block_fwd_ex(const float* x_in, const float* mass, const float* evals, const float* evecs, const dn_csr* grad,
+                    const dn_block_params* p, const dn_mesh_batch* batch, const dn_head* head, int64_t V, int K, int C,
+                    float* out, void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream) {
+  return block_fwd_impl(x_in, mass, evals, evecs, grad, p, V, K, C, out, workspace, ws_bytes, engine, stream, nullptr, batch, head);
 }
 
 int dn_mesh_batch_plan(int n_meshes, const int32_t* n_rows_host, int sm_count, int32_t* row_begin_host,

@@ -76,6 +76,12 @@ struct C3Params {
   int ring_col;    // first TMEM column of the operand ring
   int ns_shift;    // log2(ring depth): 2 -> 4 stages (32 KiB weight slots), 1 -> 2 stages (64 KiB weight slots)
   int nr_shift;    // log2(row-box slots): 2 or 1;  output staging buffers = nio - slots
+  // linear head behind the LAST layer (DnLayer::head_*): its N-wide output row is consumed in registers, not stored
+  const float* head_w;
+  const float* head_b;
+  float* head_out;
+  int64_t ld_head_out;
+  int head_n;
   int nio;         // 16 KiB row-box + staging buffers in front of the weight ring: 6 (weight ring 128 KiB) or 8 (96 KiB)
   int pair;        // 1: the MMA warp takes ring stages in pairs (4-slot rings only)
   int64_t V;
@@ -147,6 +153,7 @@ __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, fl
     }                                                                                  \
   } while (0)
 
+template <bool HEAD>     // HEAD: the fused linear head path exists (its accumulators would cost the common path registers)
 __global__ void __launch_bounds__(C3_THREADS, 1)
 rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C3Maps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -549,6 +556,12 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
         }
         const bool res = Lr.has_res != 0;
         const float rs = (Lr.row_scale && row < p.V) ? __ldg(Lr.row_scale + row) : 1.f;
+        const bool head = HEAD && p.head_w != nullptr && l + 1 == L;
+        float ho[8];
+        if (head) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) ho[o] = (o < p.head_n && p.head_b) ? __ldg(p.head_b + o) : 0.f;
+        }
         C3_TRACE(30);
         if (!res) {
           mbar_wait(do_full + 8 * buf, use & 1u);
@@ -633,6 +646,29 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
                 }
               }
             }
+            if (head) {
+              // the fused linear head: this lane's row, 32 more input channels; the weights are uniform-address loads
+#pragma unroll
+              for (int o = 0; o < 8; ++o) {
+                if (o < p.head_n) {
+                  const float4* wr = reinterpret_cast<const float4*>(p.head_w + (int64_t)o * Lr.N + c * C3_KS);
+                  float a = ho[o];
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) {
+                    const float4 w = __ldg(wr + jj);
+                    a = fmaf(w.x, v[4 * jj], a); a = fmaf(w.y, v[4 * jj + 1], a);
+                    a = fmaf(w.z, v[4 * jj + 2], a); a = fmaf(w.w, v[4 * jj + 3], a);
+                  }
+                  ho[o] = a;
+                }
+              }
+              if (res) {                                         // the residual slice was only read: it may be reloaded
+                consume_loaded(__float_as_uint(ho[0]));
+                __syncwarp();
+              }
+              C3_TRACE(35);
+              continue;
+            }
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj)
               sts128(rowaddr + ((((uint32_t)jj) ^ swz) << 4), v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
@@ -645,6 +681,12 @@ rows_chain3_kernel(const __grid_constant__ C3Params p, const __grid_constant__ C
             __syncwarp();
             C3_TRACE(35);
           }
+        }
+        if (head && row < p.V) {
+          float* orow = p.head_out + row * p.ld_head_out;
+#pragma unroll
+          for (int o = 0; o < 8; ++o)
+            if (o < p.head_n) orow[o] = ho[o];
         }
       }
     }
@@ -733,7 +775,16 @@ int tc_chain3_supported(const DnRowsSrc& src, const DnLayer* layers, int n_layer
     if (l > 0 && L.K != layers[l - 1].N) return DN_ERR_UNSUPPORTED;
     if (L.N > nmax) nmax = L.N;
   }
-  if (!layers[n_layers - 1].out) return DN_ERR_UNSUPPORTED;
+  {
+    const DnLayer& Ll = layers[n_layers - 1];
+    if (Ll.head_w) {
+      if (!Ll.head_out || Ll.head_n < 1 || Ll.head_n > 8 || Ll.dots_src || Ll.relu_mask_src ||
+          (reinterpret_cast<uintptr_t>(Ll.head_w) & 15))
+        return DN_ERR_UNSUPPORTED;
+    } else if (!Ll.out) {
+      return DN_ERR_UNSUPPORTED;
+    }
+  }
   // TMEM plans: all N <= 128 | {N0 <= 128, N1 <= 256} | single layer N <= 256
   if (nmax > 128 && !(n_layers == 1 || (n_layers == 2 && layers[0].N <= 128))) return DN_ERR_UNSUPPORTED;
   return DN_OK;
@@ -748,7 +799,8 @@ int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, in
   if (dev < 0 || dev >= kMaxDev) return DN_ERR_UNSUPPORTED;
   if (g_attr_dev[dev] == 0) {                                      // function attributes are per device
     g_attr_dev[dev] =
-        cudaFuncSetAttribute(rows_chain3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM) == cudaSuccess ? 1 : -1;
+        (cudaFuncSetAttribute(rows_chain3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM) == cudaSuccess &&
+         cudaFuncSetAttribute(rows_chain3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM) == cudaSuccess) ? 1 : -1;
     if (g_attr_dev[dev] < 0) cudaGetLastError();
   }
   if (g_attr_dev[dev] < 0) return DN_ERR_UNSUPPORTED;
@@ -768,6 +820,10 @@ int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, in
   p.trace = trace;
   p.tile_group = layers[0].tile_group;
   p.group_stride = layers[0].group_stride;
+  {
+    const DnLayer& Ll = layers[n_layers - 1];
+    p.head_w = Ll.head_w; p.head_b = Ll.head_b; p.head_out = Ll.head_out; p.ld_head_out = Ll.ld_head_out; p.head_n = Ll.head_n;
+  }
   p.nsrc = src.nsrc;
   int nmax = 0;
   for (int s = 0; s < src.nsrc; ++s) {
@@ -779,7 +835,7 @@ int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, in
     C3Layer& T = p.layer[l];
     if (!L.prepacked) return DN_ERR_INVALID_ARGUMENT;
     T.wpack = L.prepacked; T.bias = L.bias; T.row_scale = L.row_scale; T.K = L.K; T.N = L.N; T.relu = L.relu;
-    T.has_out = L.out != nullptr;
+    T.has_out = L.out != nullptr || (l + 1 == n_layers && L.head_w != nullptr);
     T.has_res = L.residual ? 1 : (L.relu_mask_src ? 2 : (L.dots_src ? 3 : 0));
     T.gy_col = L.dots_gy_col;
     if (L.dots_src) {     // output is N/2 wide; gX / gY boxes come from dots_src (any width >= gy_col + N/2)
@@ -819,7 +875,8 @@ int tc_rows_chain3(const DnRowsSrc& src, const DnLayer* layers, int n_layers, in
 
   const int64_t ntiles = (V + C3_TILE - 1) / C3_TILE;
   const int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
-  rows_chain3_kernel<<<grid, C3_THREADS, C3_SMEM, st>>>(p, maps);
+  if (p.head_w) rows_chain3_kernel<true><<<grid, C3_THREADS, C3_SMEM, st>>>(p, maps);
+  else rows_chain3_kernel<false><<<grid, C3_THREADS, C3_SMEM, st>>>(p, maps);
   DN_LAUNCH_CHECK();
   return DN_OK;
 }

@@ -557,7 +557,7 @@ int tc_chain16_supported(const DnRowsSrc& src, const DnLayer* layers, int n_laye
     const DnLayer& L = layers[l];
     const bool last = (l + 1 == n_layers);
     if (L.K % H_KS || L.K < H_KS || L.N % 32 || L.N < 32 || L.N > 256) return DN_ERR_UNSUPPORTED;
-    if (L.emul || L.dots_src) return DN_ERR_UNSUPPORTED;
+    if (L.emul || L.dots_src || L.head_w) return DN_ERR_UNSUPPORTED;
     if (L.relu_mask_src && (!last || L.residual || (reinterpret_cast<uintptr_t>(L.relu_mask_src) & 15)))
       return DN_ERR_UNSUPPORTED;
     if (L.bias && (reinterpret_cast<uintptr_t>(L.bias) & 15)) return DN_ERR_UNSUPPORTED;

@@ -59,6 +59,14 @@ struct DnLayer {
   int dots_gy_col;
   // weights given as the pair (W = A_re, W2 = A_im) of SpatialGradientFeatures acting on [gX | gY]: see PackJob::rot_C
   int rot_C, rot_ch0;
+  // linear head fused behind the last layer's epilogue (DiffusionNet.last_lin, layers.py:366-370): after bias / residual the
+  // N-wide row y is NOT stored (out may be null); head_out[v][o] = head_b[o] + sum_n head_w[o][n] * y[n], o < head_n <= 8,
+  // exact fp32 FMAs in the output warps
+  const float* head_w;
+  const float* head_b;
+  float* head_out;
+  int64_t ld_head_out;
+  int head_n;
 };
 
 #ifdef __CUDACC__

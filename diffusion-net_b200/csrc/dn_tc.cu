@@ -1176,7 +1176,7 @@ static int tc_rows_chain_legacy_supported(const DnRowsSrc& src, const DnLayer* l
   for (int l = 0; l < n_layers; ++l) {
     const DnLayer& L = layers[l];
     if (L.K % 16 || L.K < 16 || L.N % 16 || L.N < 16 || L.N > 256) return DN_ERR_UNSUPPORTED;
-    if (L.emul || L.relu_mask_src || L.dots_src) return DN_ERR_UNSUPPORTED;
+    if (L.emul || L.relu_mask_src || L.dots_src || L.head_w) return DN_ERR_UNSUPPORTED;
     if (L.bias && (reinterpret_cast<uintptr_t>(L.bias) & 15)) return DN_ERR_UNSUPPORTED;
     if (L.residual && (L.res_scale != 1.f || L.ld_res % 4 || (reinterpret_cast<uintptr_t>(L.residual) & 15)))
       return DN_ERR_UNSUPPORTED;

@@ -90,6 +90,9 @@ class SpatialGradientFeatures(nn.Module):
         return torch.stack(outs, 0).reshape(lead + outs[0].shape)
 
 
+FUSE_HEAD = True     # DiffusionNet: compute last_lin in the last block's MiniMLP epilogue when possible (inference)
+
+
 class MiniMLP(nn.Sequential):
     """[Linear, ReLU, (Dropout .5)]* Linear, with the reference submodule names (layers.py:133-164)."""
 
@@ -148,7 +151,7 @@ class DiffusionNetBlock(nn.Module):
             self.MLP_C += self.C_width
         self.mlp = MiniMLP([self.MLP_C] + self.mlp_hidden_dims + [self.C_width], dropout=self.dropout)
 
-    def _forward_mesh(self, x_in, mass, evals, evecs, gops, fused):
+    def _forward_mesh(self, x_in, mass, evals, evecs, gops, fused, head=None):
         A_re = A_im = None
         if self.with_gradient_features:
             A_re, A_im = self.gradient_features.weights()
@@ -156,14 +159,18 @@ class DiffusionNetBlock(nn.Module):
             lins = self.mlp.linears()
             return ops.block_forward_raw(x_in, mass, evals, evecs, gops, self.diffusion.diffusion_time, A_re, A_im,
                                          [l.weight for l in lins], [l.bias for l in lins],
-                                         self.with_gradient_features)
+                                         self.with_gradient_features, head=head)
+        if head is not None:
+            raise ops.HeadNotFused()
         x_diffuse = self.diffusion(x_in, None, mass, evals, evecs)
         srcs = [x_in, x_diffuse]
         if self.with_gradient_features:
             srcs.append(ops.GradFeaturesFn.apply(x_diffuse, A_re, A_im, gops))
         return self.mlp.forward_sources(srcs, residual=x_in)   # layers.py:229-239
 
-    def forward(self, x_in, mass, L, evals, evecs, gradX, gradY):
+    def forward(self, x_in, mass, L, evals, evecs, gradX, gradY, head=None):
+        """Reference signature (layers.py:200); ``head=(weight, bias)`` is this package's extension: a linear head fused
+        behind the block in inference (returns the head's output; raises ops.HeadNotFused when it cannot be fused)."""
         B = x_in.shape[0]
         if x_in.shape[-1] != self.C_width:  # reference layers.py:204-207
             raise ValueError(
@@ -185,7 +192,9 @@ class DiffusionNetBlock(nn.Module):
         params_need_grad = any(p.requires_grad for p in self.parameters())
         needs_grad = torch.is_grad_enabled() and (x_in.requires_grad or params_need_grad)
         fused = (not needs_grad) and self.mlp._fused_ok and not (self.training and self.dropout)
-        outs = [self._forward_mesh(x_in[b], mass[b], evals[b], evecs[b], gops[b], fused) for b in range(B)]
+        if head is not None and not fused:
+            raise ops.HeadNotFused()
+        outs = [self._forward_mesh(x_in[b], mass[b], evals[b], evecs[b], gops[b], fused, head) for b in range(B)]
         return torch.stack(outs, dim=0)
 
 
@@ -247,17 +256,27 @@ class DiffusionNet(nn.Module):
             raise ValueError("DiffusionNet was constructed with C_in={}, but x_in has last dim={}".format(
                 self.C_in, x.shape[-1]))
         x = ops.mlp_apply([x], [self.first_lin.weight], [self.first_lin.bias])
-        for blk in self.blocks:
+        fuse_head = FUSE_HEAD and ops.head_fusable(self.C_out)
+        head_done = False
+        for i_b, blk in enumerate(self.blocks):
             if blk.training and blk.dropout:
                 raise RuntimeError("forward_batch: eval mode only (dropout)")
             A_re = A_im = None
             if blk.with_gradient_features:
                 A_re, A_im = blk.gradient_features.weights()
             lins = blk.mlp.linears()
-            x = _batch.block_forward_batched_raw(batch, x, blk.diffusion.diffusion_time, A_re, A_im,
-                                                 [l.weight for l in lins], [l.bias for l in lins],
-                                                 blk.with_gradient_features)
-        x = ops.mlp_apply([x], [self.last_lin.weight], [self.last_lin.bias])
+            args = (batch, x, blk.diffusion.diffusion_time, A_re, A_im, [l.weight for l in lins], [l.bias for l in lins],
+                    blk.with_gradient_features)
+            if fuse_head and i_b + 1 == len(self.blocks):
+                try:
+                    x = _batch.block_forward_batched_raw(*args, head=(self.last_lin.weight, self.last_lin.bias))
+                    head_done = True
+                    break
+                except ops.HeadNotFused:
+                    pass
+            x = _batch.block_forward_batched_raw(*args)
+        if not head_done:
+            x = ops.mlp_apply([x], [self.last_lin.weight], [self.last_lin.bias])
         outs = batch.unpack(x)
         if self.outputs_at == 'global_mean':
             res = []
@@ -293,9 +312,19 @@ class DiffusionNet(nn.Module):
             appended_batch_dim = False
 
         x = self._linear(self.first_lin, x_in)
-        for b in self.blocks:
+        # last_lin rides in the last block's MiniMLP epilogue when it can (inference, <= 8 outputs, fused tensor-core chain):
+        # the C_width-wide output of the last block is then never written
+        fuse_head = FUSE_HEAD and len(self.blocks) > 0 and ops.head_fusable(self.C_out) and not torch.is_grad_enabled()
+        for i_b, b in enumerate(self.blocks):
+            if fuse_head and i_b + 1 == len(self.blocks):
+                try:
+                    x = b(x, mass, L, evals, evecs, gradX, gradY, head=(self.last_lin.weight, self.last_lin.bias))
+                    break
+                except ops.HeadNotFused:
+                    fuse_head = False
             x = b(x, mass, L, evals, evecs, gradX, gradY)
-        x = self._linear(self.last_lin, x)
+        if not fuse_head:
+            x = self._linear(self.last_lin, x)
 
         # remap to edges / faces / global mean: callers' side of the hot path
         if self.outputs_at in ('edges', 'faces'):

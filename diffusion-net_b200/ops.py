@@ -479,13 +479,26 @@ def spatial_gradient_features_raw(vectors, A_re, A_im):
     return out
 
 
+class HeadNotFused(RuntimeError):
+    """The linear head cannot ride in this block's MiniMLP epilogue (shape / engine outside the fused chain)."""
+
+
 PROFILE_STAGES = ("to_basis", "spectral_scale", "pack_weights", "from_basis_pq", "grad_features_gather", "mlp")
 
 
+def head_fusable(n_out):
+    """``DiffusionNet.last_lin`` can ride in the last block's MiniMLP epilogue (dn_block_fwd_ex) for up to 8 outputs."""
+    return 1 <= int(n_out) <= 8
+
+
 def block_forward_raw(x_in, mass, evals, evecs, ops, time, A_re, A_im, weights, biases, with_features,
-                      profile=None):
+                      profile=None, head=None, batch_desc=None):
     """Fused inference forward of one block on one mesh (dn_block_fwd).  ``profile``: a list that receives the
-    per-stage device times in ms (``PROFILE_STAGES`` order; dn_block_fwd_profile, synchronises)."""
+    per-stage device times in ms (``PROFILE_STAGES`` order; dn_block_fwd_profile, synchronises).
+    ``head=(weight, bias)``: a linear head (``DiffusionNet.last_lin``) fused behind the block -- the return value is then
+    the (V, n_out) head output and the block output is never written; raises ``HeadNotFused`` when the MiniMLP is not
+    on the fused tensor-core chain (the caller applies the head separately).  ``batch_desc``: a ``_lib.dn_mesh_batch``
+    (see batch.MeshBatch) when ``x_in`` / the operators are a batch laid out as one vertex range."""
     lib = _lib.load()
     x_in, mass, evals, evecs = _f32c(x_in), _f32c(mass), _f32c(evals), _f32c(evecs)
     V, Cc = x_in.shape
@@ -507,7 +520,25 @@ def block_forward_raw(x_in, mass, evals, evecs, ops, time, A_re, A_im, weights, 
     csr = C.byref(ops.csr[0]) if ops is not None else None
     with _on(x_in):
         # the unfused MLP route carves 2 x V x max(hidden) floats: size the scratch by the widest layer
-        ws = workspace(V, K, max(Cc, max(dims[1:])), x_in.device)
+        extra = 0 if batch_desc is None else int(batch_desc.n_meshes) * K * Cc * 8
+        ws = workspace(V, K, max(Cc, max(dims[1:])), x_in.device, extra=extra)
+        if head is not None or batch_desc is not None:
+            hd, hout = None, None
+            if head is not None:
+                hw = _f32c(head[0])
+                hb = _f32c(head[1]) if head[1] is not None else None
+                hout = torch.empty(V, hw.shape[0], dtype=torch.float32, device=x_in.device)
+                hd = _lib.dn_head(hw.data_ptr(), hb.data_ptr() if hb is not None else None, int(hw.shape[0]),
+                                  hout.data_ptr(), int(hw.shape[0]))
+            rc = lib.dn_block_fwd_ex(x_in.data_ptr(), mass.data_ptr(), evals.data_ptr(), evecs.data_ptr(), csr, C.byref(prm),
+                                     C.byref(batch_desc) if batch_desc is not None else None,
+                                     C.byref(hd) if hd is not None else None, V, K, Cc,
+                                     None if head is not None else out.data_ptr(), ws.data_ptr(), ws.numel(), _engine,
+                                     _stream())
+            if rc == -2 and head is not None:      # DN_ERR_UNSUPPORTED: the chain that would carry the head is not available
+                raise HeadNotFused()
+            _lib.check(rc, "dn_block_fwd_ex")
+            return hout if head is not None else out
         if profile is not None:
             ms = (C.c_float * 6)()
             _lib.check(lib.dn_block_fwd_profile(x_in.data_ptr(), mass.data_ptr(), evals.data_ptr(), evecs.data_ptr(),

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 4
+#define DN_ABI_VERSION 5
 
 typedef void* dn_stream_t; /* cudaStream_t */
 
@@ -263,6 +263,24 @@ int dn_mesh_batch_plan(int n_meshes, const int32_t* n_rows_host, int sm_count, i
 int dn_block_fwd_batched(const float* x_in, const float* mass, const float* evals, const float* evecs,
                          const dn_csr* grad, const dn_block_params* params, const dn_mesh_batch* batch, int64_t V,
                          int K, int C, float* out, void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream);
+
+/* Linear head fused behind a block: `DiffusionNet.last_lin` (layers.py:366-370 -- the nn.Linear applied
+ * to the last block's output) computed in the epilogue of that block's MiniMLP chain, in exact fp32, so that the
+ * C_width-wide block output is never written: out_head[v][o] = bias[o] + sum_c weight[o][c] * block_out[v][c]. */
+typedef struct dn_head {
+  const float* weight;  /* (n_out, C) nn.Linear layout */
+  const float* bias;    /* (n_out) or NULL             */
+  int32_t n_out;        /* 1..8                        */
+  float* out;           /* (V, n_out), row stride ld_out floats */
+  int64_t ld_out;
+} dn_head;
+
+/* dn_block_fwd / dn_block_fwd_batched with options: `batch` may be NULL (one mesh), `head` may be NULL.  With a head, `out`
+ * (the block output) may be NULL; DN_ERR_UNSUPPORTED when the MiniMLP does not run on the fused tensor-core chain (the
+ * caller then applies the head as a separate layer). */
+int dn_block_fwd_ex(const float* x_in, const float* mass, const float* evals, const float* evecs, const dn_csr* grad,
+                    const dn_block_params* params, const dn_mesh_batch* batch, const dn_head* head, int64_t V, int K,
+                    int C, float* out, void* workspace, int64_t ws_bytes, int engine, dn_stream_t stream);
 
 #ifdef __cplusplus
 }

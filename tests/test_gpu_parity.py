@@ -482,6 +482,50 @@ def test_build_grad_on_device_vs_reference(dn):
     assert np.abs(va2[:, 1] - np.imag(gold.data)).max() <= 2e-5 * scale
 
 
+@pytest.mark.parametrize("C,K,C_out,outputs_at", [(128, 128, 8, "vertices"), (64, 64, 5, "faces"), (128, 64, 1, "global_mean")])
+def test_last_lin_fused_into_last_block(dn, C, K, C_out, outputs_at):
+    """DiffusionNet.last_lin (layers.py:366-370) computed in the epilogue of the last block's MiniMLP chain
+    (dn_block_fwd_ex, exact fp32 head) equals the separate linear layer, single mesh and batched, and the fp64 oracle
+    composition of blocks + linear."""
+    dn.set_engine("tc3x")
+    net = dn.DiffusionNet(C_in=16, C_out=C_out, C_width=C, N_block=2, dropout=False, outputs_at=outputs_at).cuda().eval()
+    with torch.no_grad():
+        for n_, p_ in net.named_parameters():
+            if n_.endswith("diffusion_time"):
+                p_.uniform_(1e-3, 0.3)
+    n, m = 30, 41
+    mass, L, evals, evecs, gX, gY = dn.synthetic.structural_operators(n, m, K, seed=5, device="cuda")
+    V = n * m
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(V, 16, generator=g).cuda()
+    faces = torch.randint(0, V, (50, 3), generator=g).cuda()
+    kw = dict(mass=mass, evals=evals, evecs=evecs, gradX=gX, gradY=gY, faces=faces)
+    try:
+        with torch.no_grad():
+            net(x, **kw)                                            # (operator prep happens on the first call)
+            l0 = dn._lib.load().dn_kernel_launch_count()
+            dn.layers.FUSE_HEAD = True
+            y1 = net(x, **kw)
+            l1 = dn._lib.load().dn_kernel_launch_count()
+            dn.layers.FUSE_HEAD = False
+            y0 = net(x, **kw)
+            l2 = dn._lib.load().dn_kernel_launch_count()
+            assert (l2 - l1) == (l1 - l0) + 1                       # the fused route saves exactly the last_lin launch
+            assert y1.shape == y0.shape
+            assert O.rel_err(y1.cpu().numpy(), y0.cpu().numpy()) < 2e-6
+            if outputs_at == "vertices":
+                mb = dn.MeshBatch([dict(mass=mass, evals=evals, evecs=evecs, gradX=gX, gradY=gY)] * 2)
+                dn.layers.FUSE_HEAD = True
+                b1 = net.forward_batch(mb, [x, x])
+                dn.layers.FUSE_HEAD = False
+                b0 = net.forward_batch(mb, [x, x])
+                for a, b_ in zip(b1, b0):
+                    assert O.rel_err(a.cpu().numpy(), b_.cpu().numpy()) < 2e-6
+                assert O.rel_err(b1[0].cpu().numpy(), y1.cpu().numpy()) < 2e-5
+    finally:
+        dn.layers.FUSE_HEAD = True
+
+
 def test_graphed_net_and_streamed_forward(dn):
     """CUDA-graph replay (launch-bound small meshes) and the host-streaming helper reproduce the eager forward."""
     dn.set_engine("tc3x")

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_header_symbols():
     assert declared == set(dn._lib.SIGNATURES), declared ^ set(dn._lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dn_abi_version() == 4
+    assert lib.dn_abi_version() == 5
     assert lib.dn_error_string(-3).decode().startswith("diffusion_net_b200: workspace")
     assert lib.dn_workspace_bytes(200000, 128, 128) > 0
     assert lib.dn_workspace_bytes(-1, 128, 128) == -1
