@@ -619,6 +619,48 @@ def test_net_training_step_and_gradient_allreduce(dn):
     assert float(min(b.diffusion.diffusion_time.min() for b in net.blocks)) >= 0.0
 
 
+def test_data_parallel_step_gradients_vs_oracle_accumulation(dn):
+    """BASELINE config 5 semantics: gradients of a 2-block net accumulated over the rank's meshes and averaged by
+    dist.allreduce_gradients (world size 1 here; the NCCL / gloo collective itself is covered by tests/test_host.py and
+    the multi-GPU bench logs) equal the mean over the same meshes of the reference's autograd gradients -- fp64 autograd
+    through the torch restatement of the reference net (oracle/dn_oracle_torch.py blocks + the two Linear layers,
+    layers.py:362-370), i.e. the reference run with gradients accumulated over the batch."""
+    import dn_oracle_torch as T
+    dn.set_engine("tc3x")
+    C, K, C_in, C_out, NB = 32, 32, 3, 4, 2
+    net = dn.DiffusionNet(C_in=C_in, C_out=C_out, C_width=C, N_block=NB, dropout=False).cuda().train()
+    with torch.no_grad():
+        for n_, p_ in net.named_parameters():
+            if n_.endswith("diffusion_time"):
+                p_.uniform_(1e-3, 0.3)
+    meshes = []
+    for i in range(2):
+        ops_t = dn.synthetic.structural_operators(14 + i, 16, K, seed=i, device="cuda")
+        g = torch.Generator().manual_seed(20 + i)
+        V = (14 + i) * 16
+        meshes.append((torch.randn(V, C_in, generator=g).cuda(), torch.randint(0, C_out, (V,), generator=g).cuda(), ops_t))
+    for p_ in net.parameters():
+        p_.grad = None
+    for x, y, (mass, L, evals, evecs, gX, gY) in meshes:
+        out = net(x, mass, evals=evals, evecs=evecs, gradX=gX, gradY=gY)
+        torch.nn.functional.cross_entropy(out, y).backward()
+    dn.dist.allreduce_gradients(list(net.parameters()), n_global_meshes=len(meshes))
+    # gold: fp64, CPU, the reference's composition; mean of the per-mesh gradients
+    d = torch.float64
+    prm = {k: v.detach().cpu().to(d).requires_grad_(True) for k, v in net.state_dict().items()}
+    for x, y, (mass, L, evals, evecs, gX, gY) in meshes:
+        h = torch.addmm(prm["first_lin.bias"], x.cpu().to(d), prm["first_lin.weight"].t()).unsqueeze(0)
+        for b in range(NB):
+            bp = {k[len("block_%d." % b):]: v for k, v in prm.items() if k.startswith("block_%d." % b)}
+            h = T.block_forward(h, mass.cpu().to(d).unsqueeze(0), evals.cpu().to(d).unsqueeze(0),
+                                evecs.cpu().to(d).unsqueeze(0), [gX.cpu().to(d)], [gY.cpu().to(d)], bp)
+        logits = torch.addmm(prm["last_lin.bias"], h[0], prm["last_lin.weight"].t())
+        (torch.nn.functional.cross_entropy(logits, y.cpu()) / len(meshes)).backward()
+    for name, p_ in net.named_parameters():
+        assert p_.grad is not None, name
+        assert O.rel_err(p_.grad.cpu().numpy(), prm[name].grad.numpy()) < 5e-5, name
+
+
 def test_graphed_train_step_matches_eager_autograd(dn):
     """graphs.GraphedTrainStep: forward + backward of a net on one mesh replayed as one CUDA graph accumulates the same
     gradients as eager autograd (BASELINE configs 2 / 5 are launch-bound in eager mode)."""
