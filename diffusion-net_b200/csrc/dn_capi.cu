@@ -623,29 +623,6 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
   float* partial = ws.take(pf);
   if (!S || !xd || !partial || (p->with_gradient_features && (!pq || !feat))) return DN_ERR_WORKSPACE;
   int rc, P = 0;
-  mark(0);
-  // (a1) spectral diffusion: to_basis -> exp(-lambda t) -> from_basis   [layers.py:56-67]
-  if (batch) {
-    // grouped split-V: every CTA reduces a row range inside one mesh
-    if (!use_tc(engine) || !tc_supported_device() || (V % 128) || batch->n_meshes < 1 || !batch->tile_mesh ||
-        !batch->tb_rows || !batch->mesh_cta_begin || batch->n_tb_ctas < 1 || (int64_t)batch->n_tb_ctas * K * C > pf)
-      return DN_ERR_UNSUPPORTED;
-    if (tc_to_basis_supported(K, C) == DN_OK) {
-      if ((rc = tc_to_basis_partial(x_in, evecs, mass, V, K, C, partial, &P, tc_passes(engine), st, 0, 0, batch->tb_rows,
-                                    batch->n_tb_ctas)))
-        return rc;
-    } else if (C > 128 && C % 128 == 0 && tc_to_basis_supported(K, 128) == DN_OK) {
-      for (int c0 = 0; c0 < C; c0 += 128)
-        if ((rc = tc_to_basis_partial(x_in + c0, evecs, mass, V, K, 128, partial + c0, &P, tc_passes(engine), st, C, C,
-                                      batch->tb_rows, batch->n_tb_ctas)))
-          return rc;
-    } else {
-      return DN_ERR_UNSUPPORTED;
-    }
-  } else if ((rc = to_basis_partials(x_in, evecs, mass, V, K, C, partial, pf, &P, engine, st))) {
-    return rc;
-  }
-  mark(1);
 
   // every dense layer of the block: [0] from_basis, [1] (a5, commuted) [P|Q] = x_diffuse [A_re;A_im]^T,
   // [2..] cat -> MiniMLP -> + x_in  [layers.py:229-239]
@@ -729,6 +706,30 @@ static int block_fwd_impl(const float* x_in, const float* mass, const float* eva
   // the spectral multiplier S = exp(-lambda t) * (reduced partial sums) is layer 0's weight: when the tensor-core path
   // takes the front chain it is formed inside the pack launch (no separate scale kernel, S never round-trips HBM)
   if (batch && !tc_front) return DN_ERR_UNSUPPORTED;
+  // (nothing has been launched up to here: an unsupported head / batch returns before any work is enqueued)
+  mark(0);
+  // (a1) spectral diffusion: to_basis -> exp(-lambda t) -> from_basis   [layers.py:56-67]
+  if (batch) {
+    // grouped split-V: every CTA reduces a row range inside one mesh
+    if (!use_tc(engine) || !tc_supported_device() || (V % 128) || batch->n_meshes < 1 || !batch->tile_mesh ||
+        !batch->tb_rows || !batch->mesh_cta_begin || batch->n_tb_ctas < 1 || (int64_t)batch->n_tb_ctas * K * C > pf)
+      return DN_ERR_UNSUPPORTED;
+    if (tc_to_basis_supported(K, C) == DN_OK) {
+      if ((rc = tc_to_basis_partial(x_in, evecs, mass, V, K, C, partial, &P, tc_passes(engine), st, 0, 0, batch->tb_rows,
+                                    batch->n_tb_ctas)))
+        return rc;
+    } else if (C > 128 && C % 128 == 0 && tc_to_basis_supported(K, 128) == DN_OK) {
+      for (int c0 = 0; c0 < C; c0 += 128)
+        if ((rc = tc_to_basis_partial(x_in + c0, evecs, mass, V, K, 128, partial + c0, &P, tc_passes(engine), st, C, C,
+                                      batch->tb_rows, batch->n_tb_ctas)))
+          return rc;
+    } else {
+      return DN_ERR_UNSUPPORTED;
+    }
+  } else if ((rc = to_basis_partials(x_in, evecs, mass, V, K, C, partial, pf, &P, engine, st))) {
+    return rc;
+  }
+  mark(1);
   if (!tc_front)
     if ((rc = launch_spectral_scale(partial, P, evals, p->diffusion_time, K, C, nullptr, S, 1, st))) return rc;
   mark(2);
